@@ -1,0 +1,103 @@
+/* libttipm_b200 -- C ABI of the B200-native TT-IPM Newton-system hot path.
+ *
+ * The reference (FreditorK/Tensor-Train-Interior-Point-Method) has no FFI: the path sits
+ * behind plain Python functions.  Each entry point below replaces the
+ * reference routine cited next to it; the Python host mirror
+ * (tensor-train-interior-point-method_b200/ttipm_b200, src/, cy_src/) binds them with ctypes.
+ *
+ * Conventions: all arrays are float64 in DEVICE memory, row-major unless strides are given;
+ * strides are in elements; `stream` is a cudaStream_t (NULL = default stream); every call
+ * is asynchronous on `stream`; return value 0 = ok, otherwise ttipm_last_error() describes
+ * the failure.  No torch types cross this boundary.
+ */
+#ifndef TTIPM_H
+#define TTIPM_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTIPM_MAX_TERMS 16
+#define TTIPM_ABI_VERSION 1
+
+int ttipm_abi_version(void);
+const char* ttipm_last_error(void);
+/* number of SMs / max opt-in shared memory per block of the current device (0 on failure) */
+int ttipm_device_info(int* sm_count, int* smem_optin_bytes);
+
+/* One projected operator block  P1[l,s,r] * A[s,m,n,S] * P2[L,S,R]  of the local KKT system.
+ * The strides address the LOGICAL axes, so transposed / permuted operands
+ * (reference src/tt_als.py:196 'lsr,smnS,LSR,lmL->rnR', :208 'snmS', :221 'RSL', :234 'rsl')
+ * are expressed by permuting strides instead of copying. */
+typedef struct ttipm_term {
+    const double* P1;
+    const double* A;
+    const double* P2;
+    int64_t p1_strides[3]; /* (l, s, r) */
+    int64_t a_strides[4];  /* (s, m, n, S) */
+    int64_t p2_strides[3]; /* (L, S, R) */
+    int32_t s, S;
+    int32_t in_block, out_block;
+    double alpha;
+} ttipm_term;
+
+/* K1 -- y[:, i] = sum over terms with out_block == i of alpha * (P1 A P2) x[:, in_block]
+ * Replaces TTBlockMatrixView.block_local_product / compressed_ / lcompressed_ / rcompressed_
+ * (reference src/tt_als.py:190-238).  x block j element (rho, nu, Rho) lives at
+ * x[batch*x_batch_stride + j*x_block_stride + rho*x_row_stride + nu*R + Rho]; y likewise with (l, L).
+ * Output blocks without a term are zero-filled.  If `sub` != NULL the kernel stores y - sub
+ * (sub has y's layout, no batch stride).  If `sumsq` != NULL it receives, per batch entry,
+ * nb_out*L partial sums of squares of the stored values (sum them for the squared norm). */
+int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, int L, int r, int R, int nmode, int nb_out,
+                       const double* x, int64_t x_block_stride, int64_t x_row_stride, int64_t x_batch_stride,
+                       double* y, int64_t y_block_stride, int64_t y_row_stride, int64_t y_batch_stride,
+                       const double* sub, double* sumsq, int nbatch, void* stream);
+
+/* K4 -- diag[l,m,L] = sum_s,S P1[l,s,l] A[s,m,m,S] P2[L,S,L]   (reference src/tt_ipm.py:191, :292);
+ * if invert != 0 stores 1/diag (the inv_I of the Schur reduction). */
+int ttipm_local_diag(const ttipm_term* term, int l, int L, int nmode, int invert, double* out, void* stream);
+
+/* K4 -- dense local operator  out[(l,m,L),(r,n,R)] = sum_s,S P1[l,s,r] A[s,m,n,S] P2[L,S,R]
+ * (reference src/tt_ipm.py:201-212, :301-315); out is (l*nmode*L) x (r*nmode*R) row-major. */
+int ttipm_local_dense(const ttipm_term* term, int l, int L, int r, int R, int nmode, double* out, void* stream);
+
+/* K2 -- interface updates for `nterms` stored blocks at once
+ *   forward : out[L',S,R'] = sum Phi[l,s,r] U[l,M,L'] A[s,M,N,S] V[r,N,R']   (src/tt_als.py:256-257)
+ *   backward: out[l,s,r]   = sum Phi[L,S,R] U[l,M,L]  A[s,M,N,S] V[r,N,R]    (src/tt_als.py:252-253)
+ * U is (ul, nmode, uL) and V is (vr, nmode, vR), both contiguous; A is addressed through
+ * a_strides (so the m<->n swapped cores of the transposed residual interfaces need no copy);
+ * Phi and out are contiguous. */
+typedef struct ttipm_phi_term {
+    const double* Phi;
+    const double* A;
+    double* out;
+    int64_t a_strides[4];
+    int32_t s, S;
+} ttipm_phi_term;
+int ttipm_phi_update(const ttipm_phi_term* terms, int nterms, int forward, const double* U, int ul, int uL,
+                     const double* V, int vr, int vR, int nmode, void* stream);
+
+/* K3 -- right-hand-side contractions (reference src/tt_als.py:82, :260-265, src/tt_ipm.py:187-189)
+ *   mode 0: out[r,n,R] = sum Xb1[b,r] B[b,n,B'] Xb2[B',R]      (projection; out has row stride out_row_stride)
+ *   mode 1: out[B',R]  = sum Xb1[b,r] B[b,n,B'] core[r,n,R]    (forward interface)
+ *   mode 2: out[b,r]   = sum Xb2[B',R] B[b,n,B'] core[r,n,R]   (backward interface) */
+typedef struct ttipm_rhs_term {
+    const double* Xb1;  /* (b, r)  or NULL when unused */
+    const double* B;    /* (b, n, B') */
+    const double* Xb2;  /* (B', R) or NULL when unused */
+    double* out;
+    int32_t b, Bp;
+} ttipm_rhs_term;
+int ttipm_rhs_contract(const ttipm_rhs_term* terms, int nterms, int mode, const double* core, int r, int R,
+                       int nmode, int64_t out_row_stride, void* stream);
+
+/* Generic strided batched contraction  C[b](m,n) = alpha * sum_k A[b](m,k) B[b](k,n) + beta * C[b](m,n)
+ * (the bond-absorption GEMMs K5 of SURVEY 8a', reference src/tt_als.py:360,369,382,465-509). */
+int ttipm_gemm(int M, int N, int K, double alpha, const double* A, int64_t a_rs, int64_t a_cs, int64_t a_bs,
+               const double* B, int64_t b_rs, int64_t b_cs, int64_t b_bs, double beta, double* C, int64_t c_rs,
+               int64_t c_cs, int64_t c_bs, int nbatch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

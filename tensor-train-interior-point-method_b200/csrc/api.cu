@@ -1,0 +1,103 @@
+// Error reporting, device queries and small host utilities of the C ABI.
+#include <stdlib.h>
+#include <string.h>
+#include "api_util.h"
+
+#ifdef TTIPM_EMU
+namespace emu {
+thread_local Dim3 threadIdx_, blockIdx_, blockDim_, gridDim_;
+thread_local Cta* cta = nullptr;
+}  // namespace emu
+#endif
+
+namespace ttipm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+#ifndef TTIPM_EMU
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+        return 6;
+    }
+#else
+    (void)what;
+#endif
+    return 0;
+}
+
+DevInfo dev_info() {
+    static DevInfo cached = {0, 0};
+    if (cached.sms) return cached;
+#ifdef TTIPM_EMU
+    const char* s = getenv("TTIPM_EMU_SMS");
+    cached.sms = s ? atoi(s) : 2;
+    cached.smem_optin = 227 * 1024;
+#else
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&cached.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&cached.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+#endif
+    return cached;
+}
+
+int block_threads() {
+#ifdef TTIPM_EMU
+    static int bt = 0;
+    if (!bt) {
+        const char* s = getenv("TTIPM_EMU_THREADS");
+        bt = s ? atoi(s) : 64;
+    }
+    return bt;
+#else
+    return TT_MAX_THREADS;
+#endif
+}
+
+int dev_memset(void* p, int v, size_t bytes, tt_stream_t st) {
+#ifdef TTIPM_EMU
+    (void)st;
+    memset(p, v, bytes);
+    return 0;
+#else
+    return cudaMemsetAsync(p, v, bytes, st) != cudaSuccess;
+#endif
+}
+
+int dev_copy(void* dst, const void* src, size_t bytes, tt_stream_t st) {
+#ifdef TTIPM_EMU
+    (void)st;
+    memmove(dst, src, bytes);
+    return 0;
+#else
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess;
+#endif
+}
+
+}  // namespace ttipm
+
+extern "C" int ttipm_abi_version(void) { return TTIPM_ABI_VERSION; }
+extern "C" const char* ttipm_last_error(void) { return ttipm::g_err; }
+extern "C" int ttipm_device_info(int* sm_count, int* smem_optin_bytes) {
+    ttipm::DevInfo d = ttipm::dev_info();
+    if (sm_count) *sm_count = d.sms;
+    if (smem_optin_bytes) *smem_optin_bytes = d.smem_optin;
+    return d.sms > 0 ? 0 : 1;
+}

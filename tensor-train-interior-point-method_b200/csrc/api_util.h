@@ -1,0 +1,38 @@
+// Host-side helpers shared by the C-ABI entry points.
+#pragma once
+#include <limits.h>
+#include <stdarg.h>
+#include "../../include/ttipm.h"
+#include "common.cuh"
+#include "matvec.cuh"
+
+namespace ttipm {
+
+struct DevInfo {
+    int sms;
+    int smem_optin;
+};
+DevInfo dev_info();
+int block_threads();
+int dev_memset(void* p, int v, size_t bytes, tt_stream_t st);
+int dev_copy(void* dst, const void* src, size_t bytes, tt_stream_t st);
+int fail(int code, const char* fmt, ...);
+
+static inline bool fits_int(int64_t v) { return v >= INT_MIN && v <= INT_MAX; }
+
+static inline int convert_term(const ttipm_term& in, MvTerm& out) {
+    out.P1 = in.P1; out.A = in.A; out.P2 = in.P2;
+    for (int i = 0; i < 3; ++i) {
+        if (!fits_int(in.p1_strides[i]) || !fits_int(in.p2_strides[i])) return 1;
+        out.p1s[i] = (int)in.p1_strides[i];
+        out.p2s[i] = (int)in.p2_strides[i];
+    }
+    for (int i = 0; i < 4; ++i) {
+        if (!fits_int(in.a_strides[i])) return 1;
+        out.as_[i] = (int)in.a_strides[i];
+    }
+    out.s = in.s; out.S = in.S; out.in_blk = in.in_block; out.out_blk = in.out_block; out.alpha = in.alpha;
+    return 0;
+}
+
+}  // namespace ttipm

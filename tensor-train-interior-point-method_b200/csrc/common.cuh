@@ -1,0 +1,244 @@
+// Shared device-side building blocks of libttipm_b200 (sm_100a).
+//
+//  * fp64 tensor-core (DMMA, mma.sync.m8n8k4.f64) warp tiles
+//  * tgemm: a block-cooperative "tensor-contraction GEMM" whose three axes are
+//    composite indices described by AxisMap stride pairs, so every contraction of
+//    the AMEn hot path (reference src/tt_als.py:190-265, cy_src/lgmres_cy.pyx:126-153)
+//    runs through one routine without materialised transposes
+//  * a grid barrier for the persistent cooperative kernels
+//
+// The same sources also compile as plain C++ with -DTTIPM_EMU (tests/emu): every
+// CUDA thread becomes an OS thread, which lets the CPU-only test tier execute the
+// real kernel code on tiny shapes.  The product library never defines TTIPM_EMU.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#ifdef TTIPM_EMU
+#include "emu.h"
+#else
+#include <cuda_runtime.h>
+#define TT_DEV __device__ __forceinline__
+#define TT_DEVFN __device__
+#define TT_HD __host__ __device__ __forceinline__
+#define TT_GLOBAL __global__
+#define TT_SMEM_DECL(name) extern __shared__ __align__(16) unsigned char name[]
+typedef cudaStream_t tt_stream_t;
+#endif
+
+#define TT_MAX_THREADS 256
+#define TT_WARP 32
+
+namespace ttipm {
+
+// ---------------------------------------------------------------------------
+// error reporting for the C ABI
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+// ---------------------------------------------------------------------------
+// composite-axis addressing:  off(i) = (i / n1) * s0 + (i % n1) * s1
+// ---------------------------------------------------------------------------
+struct AxisMap {
+    int n1;
+    int s0;
+    int s1;
+};
+#define TT_AX_BIG (1 << 30)
+TT_DEV AxisMap ax1(int stride) { return AxisMap{TT_AX_BIG, 0, stride}; }
+TT_DEV AxisMap ax2(int n1, int s0, int s1) { return AxisMap{n1, s0, s1}; }
+TT_DEV int axoff(const AxisMap& a, int i) { return (i / a.n1) * a.s0 + (i % a.n1) * a.s1; }
+
+// ---------------------------------------------------------------------------
+// DMMA 8x8x4:  D(8x8) += A(8x4, row) * B(4x8, col)
+//   a : A[lane/4][lane%4]       b : B[lane%4][lane/4]
+//   c0,c1 : C[lane/4][2*(lane%4) + {0,1}]
+// ---------------------------------------------------------------------------
+#ifndef TTIPM_EMU
+TT_DEV void dmma884(double a, double b, double& c0, double& c1) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+TT_DEV double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+TT_DEV unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+TT_DEV double ld_cg(const double* p) { return __ldcg(p); }
+TT_DEV int ld_cg_i(const int* p) { return __ldcg(p); }
+#endif
+
+// ---------------------------------------------------------------------------
+// block-wide sum (deterministic order), scratch: >= 32 doubles of shared memory
+// ---------------------------------------------------------------------------
+TT_DEV double block_sum(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += scratch[w];
+    __syncthreads();
+    return t;
+}
+
+// ---------------------------------------------------------------------------
+// grid barrier (cooperative launch guarantees co-residency).  `counter` is a
+// zero-initialised device word; `epoch` is a per-thread running target.
+// ---------------------------------------------------------------------------
+TT_DEV void grid_sync(unsigned* counter, unsigned& epoch) {
+    if (gridDim.x == 1) {
+        __syncthreads();
+        return;
+    }
+    __syncthreads();
+    epoch += gridDim.x;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (ld_acquire_u32(counter) < epoch) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// tgemm:  C(m, n) = sum_k A(m, k) * B(k, n)   for m < M, n < N, k < K
+//   A element = A[axoff(aM, m) + axoff(aK, k)],  B element = B[axoff(bK, k) + axoff(bN, n)]
+//   store(m, n, value) is called exactly once per output element.
+//   offs: shared-memory scratch of at least (M + 2*K + N) ints.
+// All threads of the block must call it; it synchronises the block on entry and exit.
+// ---------------------------------------------------------------------------
+template <int MI, int NI, class Store>
+TT_DEV void tgemm_tiles(int M, int N, int K, const double* __restrict__ A, const double* __restrict__ B,
+                        const int* oAM, const int* oAK, const int* oBK, const int* oBN, Store store) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int TMs = 8 * MI, TNs = 8 * NI;
+    const int tm = (M + TMs - 1) / TMs, tn = (N + TNs - 1) / TNs;
+    for (int tile = wid; tile < tm * tn; tile += nw) {
+        const int m0 = (tile / tn) * TMs, n0 = (tile % tn) * TNs;
+        double acc[MI][NI][2];
+        int am[MI], bn[NI];
+        bool amok[MI], bnok[NI];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const int m = m0 + 8 * i + g;
+            amok[i] = m < M;
+            am[i] = amok[i] ? oAM[m] : 0;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+            const int n = n0 + 8 * j + g;
+            bnok[j] = n < N;
+            bn[j] = bnok[j] ? oBN[n] : 0;
+        }
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            const int k = k0 + t;
+            const bool kok = k < K;
+            const int ak = kok ? oAK[k] : 0, bk = kok ? oBK[k] : 0;
+            double a[MI], b[NI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) a[i] = (kok && amok[i]) ? A[am[i] + ak] : 0.0;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) b[j] = (kok && bnok[j]) ? B[bk + bn[j]] : 0.0;
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma884(a[i], b[j], acc[i][j][0], acc[i][j][1]);
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const int m = m0 + 8 * i + g;
+            if (m < M) {
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    const int n = n0 + 8 * j + 2 * t;
+                    if (n < N) store(m, n, acc[i][j][0]);
+                    if (n + 1 < N) store(m, n + 1, acc[i][j][1]);
+                }
+            }
+        }
+    }
+}
+
+template <class Store>
+TT_DEV void tgemm(int M, int N, int K, const double* __restrict__ A, AxisMap aM, AxisMap aK,
+                  const double* __restrict__ B, AxisMap bK, AxisMap bN, Store store, int* offs) {
+    int* oAM = offs;
+    int* oAK = oAM + M;
+    int* oBK = oAK + K;
+    int* oBN = oBK + K;
+    __syncthreads();
+    for (int i = threadIdx.x; i < M; i += blockDim.x) oAM[i] = axoff(aM, i);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        oAK[i] = axoff(aK, i);
+        oBK[i] = axoff(bK, i);
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) oBN[i] = axoff(bN, i);
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    // pick the warp tile so that every warp gets work and skinny axes are not over-padded
+    const bool wideM = M > 8 && ((M + 15) / 16) * ((N + 7) / 8) >= nw;
+    const bool wideN = N > 8 && ((M + 7) / 8) * ((N + 15) / 16) >= nw;
+    if (wideM && wideN && ((M + 15) / 16) * ((N + 15) / 16) >= nw)
+        tgemm_tiles<2, 2>(M, N, K, A, B, oAM, oAK, oBK, oBN, store);
+    else if (wideM)
+        tgemm_tiles<2, 1>(M, N, K, A, B, oAM, oAK, oBK, oBN, store);
+    else if (wideN)
+        tgemm_tiles<1, 2>(M, N, K, A, B, oAM, oAK, oBK, oBN, store);
+    else
+        tgemm_tiles<1, 1>(M, N, K, A, B, oAM, oAK, oBK, oBN, store);
+    __syncthreads();
+}
+
+TT_HD int align_up(int v, int a) { return (v + a - 1) / a * a; }
+TT_HD int imin(int a, int b) { return a < b ? a : b; }
+TT_HD int imax(int a, int b) { return a > b ? a : b; }
+
+// ---------------------------------------------------------------------------
+// launch helper: every kernel takes ONE parameter struct by value
+// ---------------------------------------------------------------------------
+template <class P>
+int launch_kernel(const char* name, void (*kern)(P), dim3 grid, dim3 block, size_t smem, tt_stream_t st, bool coop,
+                  const P& params) {
+#ifdef TTIPM_EMU
+    (void)name;
+    (void)st;
+    ::emu::launch(grid, block, smem, coop, [&]() { kern(params); });
+    return 0;
+#else
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("%s: cannot opt in to %zu B of shared memory: %s", name, smem, cudaGetErrorString(e));
+            return 2;
+        }
+    }
+    if (coop) {
+        void* args[] = {(void*)&params};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, grid, block, args, smem, st);
+        if (e != cudaSuccess) {
+            set_error("%s: cooperative launch failed: %s", name, cudaGetErrorString(e));
+            return 3;
+        }
+        return 0;
+    }
+    kern<<<grid, block, smem, st>>>(params);
+    return check_launch(name);
+#endif
+}
+
+}  // namespace ttipm

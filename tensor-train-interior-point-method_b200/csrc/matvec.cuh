@@ -1,0 +1,121 @@
+// K1: the AMEn local block matvec  y[l,m,L] = sum P1[l,s,r] A[s,m,n,S] P2[L,S,R] x[r,n,R]
+// (reference src/tt_als.py:190-238, cy_src/lgmres_cy.pyx:126-153) as a fused 3-stage DMMA
+// chain per (output block, L-tile) work item.  Operands are addressed through strides, so
+// the transposed apply ('lsr,smnS,LSR,lmL->rnR') and the permuted residual-interface
+// variants ('snmS', 'RSL', 'rsl') need no materialised transposes.
+#pragma once
+#include "common.cuh"
+
+namespace ttipm {
+
+struct MvTerm {
+    const double* P1;   // logical (l, s, r) through p1s
+    const double* A;    // logical (s, m, n, S) through as_
+    const double* P2;   // logical (L, S, R) through p2s
+    int p1s[3];
+    int as_[4];
+    int p2s[3];
+    int s, S;
+    int in_blk, out_blk;
+    double alpha;
+};
+
+// geometry + shared-memory carve-up of one work item; filled on the host by mv_plan()
+struct MvGeom {
+    int l, L, r, R, nm;     // output ranks (l, L), input ranks (r, R), mode size (m = n)
+    int Lt, ntiles;         // L-tile width, number of tiles
+    int smax, Smax;
+    int ld1, ld2, ldA, ldY; // leading dimensions of T1, T2, As, Ys
+    int oT1, oT2, oAs, oYs, oOffs;   // offsets in doubles from the shared base (oOffs too)
+    int smem_bytes;
+};
+
+static inline int mv_pad(int v, int rem, int mod) {   // smallest w >= v with w % mod == rem
+    int w = v;
+    while (w % mod != rem) ++w;
+    return w;
+}
+
+// Host: choose the tile width and lay out shared memory.  target_ctas is the number of
+// co-resident CTAs one wants to fill (148 SMs on B200); returns 0 or an error.
+static inline int mv_plan(MvGeom& g, int l, int L, int r, int R, int nm, int smax, int Smax, int nb_out,
+                          int target_ctas, int smem_limit) {
+    g.l = l; g.L = L; g.r = r; g.R = R; g.nm = nm; g.smax = smax; g.Smax = Smax;
+    int Lt = (L * nb_out + target_ctas - 1) / target_ctas;
+    if (Lt < 1) Lt = 1;
+    if (Lt > L) Lt = L;
+    for (;;) {
+        g.Lt = Lt;
+        g.ntiles = (L + Lt - 1) / Lt;
+        g.ld1 = mv_pad(nm * Smax, 4, 8);
+        g.ld2 = mv_pad(nm * Lt, 0, 2) + ((nm * Lt) % 16 == 0 ? 8 : 0);
+        g.ldA = mv_pad(smax * nm, 0, 2) + ((smax * nm) % 16 == 0 ? 8 : 0);
+        g.ldY = nm * Lt;
+        int nT1 = r * Lt * g.ld1, nT2 = smax * r * g.ld2, nAs = nm * Smax * g.ldA, nYs = l * g.ldY;
+        int m1 = r * nm, m2 = r * Lt, m3 = l;
+        int k1 = R, k2 = nm * Smax, k3 = smax * r;
+        int n1 = Lt * Smax, n2 = smax * nm, n3 = nm * Lt;
+        int mM = m1 > m2 ? m1 : m2; if (m3 > mM) mM = m3;
+        int mK = k1 > k2 ? k1 : k2; if (k3 > mK) mK = k3;
+        int mN = n1 > n2 ? n1 : n2; if (n3 > mN) mN = n3;
+        int nOffs = (mM + 2 * mK + mN + 1) / 2;     // ints, counted in doubles
+        g.oT1 = 0;
+        g.oT2 = g.oT1 + nT1;
+        g.oAs = g.oT2 + nT2;
+        g.oYs = g.oAs + nAs;
+        g.oOffs = g.oYs + nYs;
+        g.smem_bytes = (g.oOffs + nOffs + 40) * 8;
+        if (g.smem_bytes <= smem_limit) return 0;
+        if (Lt == 1) return 1;
+        Lt = Lt / 2;
+    }
+}
+
+#if defined(__CUDACC__) || defined(TTIPM_EMU)
+// Accumulate alpha * (term applied to x_blk) for L-tile [L0, L0+Ltc) into Ys (l x ldY, column (m, Lt)).
+//   x_blk: element (rho, nu, Rho) at x_blk[rho * x_rs + nu * R + Rho]
+TT_DEV void mv_accumulate_term(const MvTerm& t, const double* __restrict__ x_blk, int x_rs, const MvGeom& g,
+                               int L0, int Ltc, double* smem) {
+    double* T1 = smem + g.oT1;
+    double* T2 = smem + g.oT2;
+    double* As = smem + g.oAs;
+    double* Ys = smem + g.oYs;
+    int* offs = (int*)(smem + g.oOffs);
+    const int r = g.r, R = g.R, nm = g.nm, l = g.l, s = t.s, S = t.S;
+    const int ld1 = g.ld1, ld2 = g.ld2, ldA = g.ldA, ldY = g.ldY;
+
+    // operator core -> As[(nu, sig'), (sig, mu)]
+    for (int i = threadIdx.x; i < nm * S * s * nm; i += blockDim.x) {
+        const int col = i % (s * nm), row = i / (s * nm);
+        const int sg = col / nm, mu = col % nm, nu = row / S, sp = row % S;
+        As[row * ldA + col] = t.A[sg * t.as_[0] + mu * t.as_[1] + nu * t.as_[2] + sp * t.as_[3]];
+    }
+    // stage 1: T1[(rho, Lt), (nu, sig')] = sum_Rho x[(rho, nu), Rho] * P2[(L0 + Lt, sig'), Rho]
+    tgemm(r * nm, Ltc * S, R, x_blk, ax2(nm, x_rs, R), ax1(1),
+          t.P2 + (long)L0 * t.p2s[0], ax1(t.p2s[2]), ax2(S, t.p2s[0], t.p2s[1]),
+          [&](int m, int n, double v) {
+              const int rho = m / nm, nu = m % nm, lt = n / S, sp = n % S;
+              T1[(rho * Ltc + lt) * ld1 + nu * S + sp] = v;
+          },
+          offs);
+    // stage 2: T2[(sig, rho), (mu, Lt)] = sum_(nu, sig') T1[(rho, Lt), (nu, sig')] * As[(nu, sig'), (sig, mu)]
+    tgemm(r * Ltc, s * nm, nm * S, T1, ax1(ld1), ax1(1), As, ax1(ldA), ax1(1),
+          [&](int m, int n, double v) {
+              const int rho = m / Ltc, lt = m % Ltc, sg = n / nm, mu = n % nm;
+              T2[(sg * r + rho) * ld2 + mu * Ltc + lt] = v;
+          },
+          offs);
+    // stage 3: Ys[lam, (mu, Lt)] += alpha * sum_(sig, rho) P1[lam, sig, rho] * T2[(sig, rho), (mu, Lt)]
+    const double alpha = t.alpha;
+    tgemm(l, nm * Ltc, s * r, t.P1, ax1(t.p1s[0]), ax2(r, t.p1s[1], t.p1s[2]), T2, ax1(ld2), ax1(1),
+          [&](int m, int n, double v) { Ys[m * ldY + n] += alpha * v; }, offs);
+}
+
+TT_DEV void mv_zero_tile(const MvGeom& g, double* smem) {
+    double* Ys = smem + g.oYs;
+    for (int i = threadIdx.x; i < g.l * g.ldY; i += blockDim.x) Ys[i] = 0.0;
+    __syncthreads();
+}
+#endif
+
+}  // namespace ttipm

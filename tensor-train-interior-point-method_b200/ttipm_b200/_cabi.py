@@ -1,0 +1,61 @@
+"""ctypes declarations for include/ttipm.h."""
+import ctypes as C
+import os
+
+c_double_p = C.c_void_p   # device pointers are passed as integers
+i64 = C.c_int64
+i32 = C.c_int32
+
+MAX_TERMS = 16
+
+
+class Term(C.Structure):
+    _fields_ = [("P1", C.c_void_p), ("A", C.c_void_p), ("P2", C.c_void_p),
+                ("p1_strides", i64 * 3), ("a_strides", i64 * 4), ("p2_strides", i64 * 3),
+                ("s", i32), ("S", i32), ("in_block", i32), ("out_block", i32), ("alpha", C.c_double)]
+
+
+class PhiTerm(C.Structure):
+    _fields_ = [("Phi", C.c_void_p), ("A", C.c_void_p), ("out", C.c_void_p), ("a_strides", i64 * 4),
+                ("s", i32), ("S", i32)]
+
+
+class RhsTerm(C.Structure):
+    _fields_ = [("Xb1", C.c_void_p), ("B", C.c_void_p), ("Xb2", C.c_void_p), ("out", C.c_void_p),
+                ("b", i32), ("Bp", i32)]
+
+
+SIGNATURES = {
+    "ttipm_abi_version": (C.c_int, []),
+    "ttipm_last_error": (C.c_char_p, []),
+    "ttipm_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ttipm_block_matvec": (C.c_int, [C.POINTER(Term), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, i64, i64, i64, C.c_void_p, i64, i64, i64, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_void_p]),
+    "ttipm_local_diag": (C.c_int, [C.POINTER(Term), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ttipm_local_dense": (C.c_int, [C.POINTER(Term), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p]),
+    "ttipm_phi_update": (C.c_int, [C.POINTER(PhiTerm), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ttipm_rhs_contract": (C.c_int, [C.POINTER(RhsTerm), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, i64,
+                                     C.c_void_p]),
+    "ttipm_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, i64, i64, i64, C.c_void_p, i64, i64,
+                             i64, C.c_double, C.c_void_p, i64, i64, i64, C.c_int, C.c_void_p]),
+}
+
+DEFAULT_LIB = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "libttipm_b200.so"))
+
+
+def load(path=None):
+    path = path or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with `python tensor-train-interior-point-method_b200/build.py` "
+                           "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ttipm_abi_version() != 1:
+        raise RuntimeError("libttipm ABI version mismatch")
+    return lib

@@ -1,0 +1,195 @@
+"""Tensor-level wrappers over the C ABI (include/ttipm.h).
+
+Tensors are float64 torch tensors on the runtime's device; non-contiguous views are fine
+wherever the ABI takes strides (that is how transposed / permuted operands are expressed).
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from .runtime import get_runtime
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class TermList:
+    """A list of projected operator blocks; keeps the tensors alive while the C structs are in use."""
+
+    def __init__(self):
+        self.items = []
+
+    def add(self, P1, A, P2, in_block, out_block, alpha=1.0):
+        assert P1.dim() == 3 and A.dim() == 4 and P2.dim() == 3
+        assert P1.shape[1] == A.shape[0] and P2.shape[1] == A.shape[3], (P1.shape, A.shape, P2.shape)
+        self.items.append((P1, A, P2, int(in_block), int(out_block), float(alpha)))
+        return self
+
+    def __len__(self):
+        return len(self.items)
+
+    def carray(self):
+        n = len(self.items)
+        arr = (_cabi.Term * max(n, 1))()
+        for q, (P1, A, P2, ib, ob, alpha) in enumerate(self.items):
+            t = arr[q]
+            t.P1, t.A, t.P2 = P1.data_ptr(), A.data_ptr(), P2.data_ptr()
+            t.p1_strides[:] = list(P1.stride())
+            t.a_strides[:] = list(A.stride())
+            t.p2_strides[:] = list(P2.stride())
+            t.s, t.S = A.shape[0], A.shape[3]
+            t.in_block, t.out_block, t.alpha = ib, ob, alpha
+        return arr, n
+
+
+def block_matvec(terms, x, nb_out, out_ranks, sub=None, want_norm=False, rt=None):
+    """y[:, i] = sum_terms alpha * (P1 A P2) x[:, in_block]   (reference src/tt_als.py:190-238).
+
+    x: (r, b_in, n, R) or batched (B, r, b_in, n, R); returns y (l, nb_out, n, L) [batched likewise]
+    and, if want_norm, a device tensor with the squared norm partials (sum them on the host)."""
+    rt = rt or get_runtime()
+    batched = x.dim() == 5
+    xb = x if batched else x.unsqueeze(0)
+    B, r, b_in, n, R = xb.shape
+    assert xb.stride(4) == 1 and xb.stride(3) == R, "x needs contiguous (n, R) panels"
+    l, L = out_ranks
+    y = rt.empty(B, l, nb_out, n, L)
+    arr, nt = terms.carray()
+    for (P1, A, P2, ib, ob, _) in terms.items:
+        assert P1.shape[0] == l and P1.shape[2] == r and P2.shape[0] == L and P2.shape[2] == R, \
+            (P1.shape, P2.shape, (l, r, L, R))
+        assert A.shape[1] == n and A.shape[2] == n and ib < b_in and ob < nb_out
+    sumsq = rt.empty(B, nb_out * L) if want_norm else None
+    if sub is not None:
+        assert sub.shape == (l, nb_out, n, L) and sub.is_contiguous()
+    code = rt.lib.ttipm_block_matvec(arr, nt, l, L, r, R, n, nb_out, _ptr(xb), xb.stride(2), xb.stride(1),
+                                     xb.stride(0), _ptr(y), y.stride(2), y.stride(1), y.stride(0), _ptr(sub),
+                                     _ptr(sumsq), B, rt.stream())
+    rt.check(code, "ttipm_block_matvec")
+    if not batched:
+        y = y[0]
+    return (y, sumsq) if want_norm else y
+
+
+def local_diag(P1, A, P2, invert=False, rt=None):
+    """'lsr,smnS,LSR->lmL' (reference src/tt_ipm.py:191)."""
+    rt = rt or get_runtime()
+    tl = TermList().add(P1, A, P2, 0, 0)
+    arr, _ = tl.carray()
+    l, L, n = P1.shape[0], P2.shape[0], A.shape[1]
+    out = rt.empty(l, n, L)
+    rt.check(rt.lib.ttipm_local_diag(arr, l, L, n, int(invert), _ptr(out), rt.stream()), "ttipm_local_diag")
+    return out
+
+
+def local_dense(P1, A, P2, rt=None):
+    """'lsr,smnS,LSR->lmLrnR' as an (l n L) x (r n R) matrix (reference src/tt_ipm.py:201-212)."""
+    rt = rt or get_runtime()
+    tl = TermList().add(P1, A, P2, 0, 0)
+    arr, _ = tl.carray()
+    l, r, L, R, n = P1.shape[0], P1.shape[2], P2.shape[0], P2.shape[2], A.shape[1]
+    out = rt.empty(l * n * L, r * n * R)
+    rt.check(rt.lib.ttipm_local_dense(arr, l, L, r, R, n, _ptr(out), rt.stream()), "ttipm_local_dense")
+    return out
+
+
+def phi_update(phis, cores_A, U, V, forward, rt=None):
+    """Interface updates for several stored blocks in one launch (reference src/tt_als.py:252-257).
+
+    phis: list of Phi tensors (contiguous), cores_A: list of operator cores (any strides),
+    U: left core (ul, n, uL), V: right core (vr, n, vR).  Returns the list of new interfaces."""
+    rt = rt or get_runtime()
+    n = len(phis)
+    assert U.is_contiguous() and V.is_contiguous()
+    ul, nm, uL = U.shape
+    vr, _, vR = V.shape
+    arr = (_cabi.PhiTerm * n)()
+    outs = []
+    for q, (Phi, A) in enumerate(zip(phis, cores_A)):
+        assert Phi.is_contiguous()
+        s, S = A.shape[0], A.shape[3]
+        if forward:
+            assert Phi.shape == (ul, s, vr), (Phi.shape, (ul, s, vr))
+            out = rt.empty(uL, S, vR)
+        else:
+            assert Phi.shape == (uL, S, vR), (Phi.shape, (uL, S, vR))
+            out = rt.empty(ul, s, vr)
+        outs.append(out)
+        t = arr[q]
+        t.Phi, t.A, t.out = Phi.data_ptr(), A.data_ptr(), out.data_ptr()
+        t.a_strides[:] = list(A.stride())
+        t.s, t.S = s, S
+    code = rt.lib.ttipm_phi_update(arr, n, int(forward), _ptr(U), ul, uL, _ptr(V), vr, vR, nm, rt.stream())
+    rt.check(code, "ttipm_phi_update")
+    return outs
+
+
+def rhs_project(Xb1s, Bs, Xb2s, out, blocks, rt=None):
+    """out[:, blocks[q]] = 'br,bnB,BR->rnR' (reference src/tt_als.py:82); out: (r, nb, n, R) contiguous."""
+    rt = rt or get_runtime()
+    n = len(Bs)
+    r, nb, nm, R = out.shape
+    arr = (_cabi.RhsTerm * n)()
+    for q in range(n):
+        X1, Bc, X2 = Xb1s[q], Bs[q], Xb2s[q]
+        assert X1.is_contiguous() and Bc.is_contiguous() and X2.is_contiguous()
+        assert X1.shape == (Bc.shape[0], r) and X2.shape == (Bc.shape[2], R), (X1.shape, Bc.shape, X2.shape, out.shape)
+        t = arr[q]
+        t.Xb1, t.B, t.Xb2 = X1.data_ptr(), Bc.data_ptr(), X2.data_ptr()
+        t.out = out.data_ptr() + 8 * blocks[q] * out.stride(1)
+        t.b, t.Bp = Bc.shape[0], Bc.shape[2]
+    code = rt.lib.ttipm_rhs_contract(arr, n, 0, C.c_void_p(0), r, R, nm, out.stride(0), rt.stream())
+    rt.check(code, "ttipm_rhs_contract")
+    return out
+
+
+def phi_rhs_update(Xbs, Bs, core, forward, rt=None):
+    """'br,bnB,rnR->BR' (forward) / 'BR,bnB,rnR->br' (backward), reference src/tt_als.py:260-265."""
+    rt = rt or get_runtime()
+    n = len(Bs)
+    assert core.is_contiguous()
+    r, nm, R = core.shape
+    arr = (_cabi.RhsTerm * n)()
+    outs = []
+    for q in range(n):
+        Xb, Bc = Xbs[q], Bs[q]
+        assert Xb.is_contiguous() and Bc.is_contiguous()
+        t = arr[q]
+        t.B = Bc.data_ptr()
+        t.b, t.Bp = Bc.shape[0], Bc.shape[2]
+        if forward:
+            assert Xb.shape == (Bc.shape[0], r)
+            out = rt.empty(Bc.shape[2], R)
+            t.Xb1, t.Xb2 = Xb.data_ptr(), 0
+        else:
+            assert Xb.shape == (Bc.shape[2], R)
+            out = rt.empty(Bc.shape[0], r)
+            t.Xb1, t.Xb2 = 0, Xb.data_ptr()
+        t.out = out.data_ptr()
+        outs.append(out)
+    code = rt.lib.ttipm_rhs_contract(arr, n, 1 if forward else 2, _ptr(core), r, R, nm, 0, rt.stream())
+    rt.check(code, "ttipm_rhs_contract")
+    return outs
+
+
+def gemm(A, B, out=None, alpha=1.0, beta=0.0, rt=None):
+    """C = alpha * A @ B + beta * C for 2-D (or batched 3-D) strided views."""
+    rt = rt or get_runtime()
+    batched = A.dim() == 3
+    A3 = A if batched else A.unsqueeze(0)
+    B3 = B if B.dim() == 3 else B.unsqueeze(0)
+    nb, M, K = A3.shape
+    N = B3.shape[2]
+    assert B3.shape[1] == K
+    if out is None:
+        out = rt.empty(nb, M, N) if batched else rt.empty(M, N)
+        beta = 0.0
+    C3 = out if out.dim() == 3 else out.unsqueeze(0)
+    bs = lambda t: t.stride(0) if t.shape[0] > 1 else 0
+    code = rt.lib.ttipm_gemm(M, N, K, alpha, _ptr(A3), A3.stride(1), A3.stride(2), bs(A3), _ptr(B3), B3.stride(1),
+                             B3.stride(2), bs(B3) if B3.shape[0] == nb else 0, beta, _ptr(C3), C3.stride(1),
+                             C3.stride(2), bs(C3), nb, rt.stream())
+    rt.check(code, "ttipm_gemm")
+    return out

@@ -1,0 +1,142 @@
+"""Parity cases shared by the emulator tier (CPU) and the GPU tier: every case runs the product
+kernels through the C ABI on `rt` and compares with the oracle / the golden fixtures.
+Tolerance: 1e-10 relative in fp64 (BASELINE.json north_star)."""
+import numpy as np
+
+import golden_io as G
+import tt_oracle as O
+from ttipm_b200 import kernels as K
+
+TOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _dev(rt, d):
+    return {k: rt.to_device(v) for k, v in d.items()}
+
+
+def load_blp_case(case):
+    z = G.load("kernels.npz")
+    p = f"blp/{case}"
+    out = dict(nb=int(z[p + "/nb"]), x=z[p + "/x"], A=G.keyed(z, p + "/A"), P1=G.keyed(z, p + "/P1"),
+               P2=G.keyed(z, p + "/P2"), Z1=G.keyed(z, p + "/Z1"), Z2=G.keyed(z, p + "/Z2"), left=z[p + "/left"],
+               zleft=z[p + "/zleft"], b=G.keyed(z, p + "/b"), Xb1=G.keyed(z, p + "/Xb1"), Xb2=G.keyed(z, p + "/Xb2"),
+               inv_I=z[p + "/inv_I"], red_x=z[p + "/red_x"], red_y=z[p + "/red_y"], z=z, p=p)
+    out["aliases"] = {(1, 2): (1, 3)} if out["nb"] == 4 else {}
+    out["transposes"] = {(0, 1): (1, 0)}
+    return out
+
+
+def full_terms(rt, c, left, right, left_is_z, right_is_z):
+    """Term list of block_local_product / the compressed variants (reference src/tt_als.py:190-238)."""
+    A, Ld, Rd = _dev(rt, c["A"]), _dev(rt, left), _dev(rt, right)
+    tl = K.TermList()
+    for (i, j) in c["A"]:
+        tl.add(Ld[i, j], A[i, j], Rd[i, j], j, i)
+        if (i, j) in c["transposes"]:
+            p, t = c["transposes"][i, j]
+            Pl = Ld[p, t] if left_is_z else Ld[i, j].permute(2, 1, 0)
+            Pr = Rd[p, t] if right_is_z else Rd[i, j].permute(2, 1, 0)
+            tl.add(Pl, A[i, j].permute(0, 2, 1, 3), Pr, t, p)
+        if (i, j) in c["aliases"]:
+            p, t = c["aliases"][i, j]
+            tl.add(Ld[i, j], A[i, j], Rd[i, j], t, p)
+    return tl
+
+
+def case_block_matvec(rt, case):
+    c = load_blp_case(case)
+    z, p, nb = c["z"], c["p"], c["nb"]
+    x = rt.to_device(c["x"])
+    r, _, n, R = c["x"].shape
+    errs = {}
+    y = K.block_matvec(full_terms(rt, c, c["P1"], c["P2"], False, False), x, nb, (r, R), rt=rt)
+    errs["blp"] = rel(rt.to_host(y), z[p + "/y"])
+    for nm, (lft, rgt, lz, rz) in {"y_cc": (c["Z1"], c["Z2"], True, True), "y_lc": (c["Z1"], c["P2"], True, False),
+                                    "y_rc": (c["P1"], c["Z2"], False, True)}.items():
+        ref = z[f"{p}/{nm}"]
+        y = K.block_matvec(full_terms(rt, c, lft, rgt, lz, rz), x, nb, (ref.shape[0], ref.shape[3]), rt=rt)
+        errs[nm] = rel(rt.to_host(y), ref)
+    # residual + norm fused, batched
+    sub = rt.to_device(z[p + "/y"] * 0.5)
+    xb = rt.to_device(np.stack([c["x"], 2 * c["x"], -c["x"]]))
+    y, ss = K.block_matvec(full_terms(rt, c, c["P1"], c["P2"], False, False), xb, nb, (r, R), sub=sub,
+                           want_norm=True, rt=rt)
+    want = np.stack([z[p + "/y"] * f - 0.5 * z[p + "/y"] for f in (1, 2, -1)])
+    errs["batched_sub"] = rel(rt.to_host(y), want)
+    errs["sumsq"] = rel(rt.to_host(ss).sum(axis=1), (want.reshape(3, -1) ** 2).sum(axis=1))
+    return errs
+
+
+def case_phi(rt, case):
+    c = load_blp_case(case)
+    z, p = c["z"], c["p"]
+    keys = list(c["A"].keys())
+    A, P1, P2, Z1, Z2 = (_dev(rt, c[k]) for k in ("A", "P1", "P2", "Z1", "Z2"))
+    left, zleft = rt.to_device(c["left"]), rt.to_device(c["zleft"])
+    errs = {}
+    for nm, phis, U, fwd in (("phi_bck", P2, left, False), ("phi_fwd", P1, left, True),
+                             ("zphi_bck", Z2, zleft, False), ("zphi_fwd", Z1, zleft, True)):
+        outs = K.phi_update([phis[k] for k in keys], [A[k] for k in keys], U, left, fwd, rt=rt)
+        errs[nm] = max(rel(rt.to_host(o), z[f"{p}/{nm}/{k[0]}{k[1]}"]) for o, k in zip(outs, keys))
+    # transposed residual interface: m<->n swapped operator core through strides only
+    k01 = (0, 1)
+    At = A[k01].permute(0, 2, 1, 3)
+    o = K.phi_update([Z1[(1, 0)]], [At], zleft, left, True, rt=rt)[0]
+    errs["zphi_fwd_T"] = rel(rt.to_host(o), O.phi_fwd(c["Z1"][(1, 0)], c["zleft"], c["A"][k01].transpose(0, 2, 1, 3), c["left"]))
+    o = K.phi_update([Z2[(1, 0)]], [At], zleft, left, False, rt=rt)[0]
+    errs["zphi_bck_T"] = rel(rt.to_host(o), O.phi_bck(c["Z2"][(1, 0)], c["zleft"], c["A"][k01].transpose(0, 2, 1, 3), c["left"]))
+    return errs
+
+
+def case_rhs(rt, case):
+    c = load_blp_case(case)
+    z, p, nb = c["z"], c["p"], c["nb"]
+    b, X1, X2 = _dev(rt, c["b"]), _dev(rt, c["Xb1"]), _dev(rt, c["Xb2"])
+    left = rt.to_device(c["left"])
+    rows = sorted(c["b"].keys())
+    ref = z[p + "/rhs"]
+    out = rt.zeros(*ref.shape)
+    K.rhs_project([X1[i] for i in rows], [b[i] for i in rows], [X2[i] for i in rows], out, rows, rt=rt)
+    errs = {"rhs": rel(rt.to_host(out), ref)}
+    of = K.phi_rhs_update([X1[i] for i in rows], [b[i] for i in rows], left, True, rt=rt)
+    ob = K.phi_rhs_update([X2[i] for i in rows], [b[i] for i in rows], left, False, rt=rt)
+    errs["phib_fwd"] = max(rel(rt.to_host(o), z[f"{p}/phib_fwd/{i}"]) for o, i in zip(of, rows))
+    errs["phib_bck"] = max(rel(rt.to_host(o), z[f"{p}/phib_bck/{i}"]) for o, i in zip(ob, rows))
+    return errs
+
+
+def case_diag_dense(rt, case):
+    c = load_blp_case(case)
+    errs = {}
+    for key in list(c["A"].keys())[:3]:
+        P1, A, P2 = (rt.to_device(c[k][key]) for k in ("P1", "A", "P2"))
+        errs[f"diag{key}"] = rel(rt.to_host(K.local_diag(P1, A, P2, rt=rt)), O.local_diag(c["P1"][key], c["A"][key], c["P2"][key]))
+        errs[f"inv{key}"] = rel(rt.to_host(K.local_diag(P1, A, P2, invert=True, rt=rt)),
+                                1.0 / O.local_diag(c["P1"][key], c["A"][key], c["P2"][key]))
+        errs[f"dense{key}"] = rel(rt.to_host(K.local_dense(P1, A, P2, rt=rt)), O.local_dense(c["P1"][key], c["A"][key], c["P2"][key]))
+    return errs
+
+
+def case_gemm(rt):
+    rng = np.random.default_rng(3)
+    errs = {}
+    for (M, N, Kd) in ((5, 7, 3), (33, 17, 70), (64, 130, 9), (1, 1, 1)):
+        a, b, c0 = rng.standard_normal((M, Kd)), rng.standard_normal((Kd, N)), rng.standard_normal((M, N))
+        out = rt.to_device(c0)
+        K.gemm(rt.to_device(a), rt.to_device(b), out=out, alpha=0.5, beta=2.0, rt=rt)
+        errs[f"g{M}x{N}x{Kd}"] = rel(rt.to_host(out), 0.5 * a @ b + 2 * c0)
+        at = rt.to_device(a.T.copy()).t()          # strided view
+        errs[f"gt{M}x{N}x{Kd}"] = rel(rt.to_host(K.gemm(at, rt.to_device(b), rt=rt)), a @ b)
+    a, b = rng.standard_normal((3, 6, 5)), rng.standard_normal((3, 5, 4))
+    errs["batched"] = rel(rt.to_host(K.gemm(rt.to_device(a), rt.to_device(b), rt=rt)), a @ b)
+    return errs
+
+
+def assert_small(errs, tol=TOL):
+    bad = {k: v for k, v in errs.items() if not (v <= tol)}
+    assert not bad, f"parity failures (rel err > {tol}): {bad}; all: {errs}"

@@ -1,0 +1,36 @@
+"""CPU tier: the REAL kernel sources, compiled with -DTTIPM_EMU (threads = OS threads), against
+the oracle and the reference-generated fixtures.  Small shapes only."""
+import pytest
+
+import rt_util
+import kernel_cases as KC
+
+CASES = ["eq_small", "ineq_small"]
+
+
+@pytest.fixture(scope="module")
+def rt():
+    return rt_util.emu_runtime()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_block_matvec(rt, case):
+    KC.assert_small(KC.case_block_matvec(rt, case))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_phi(rt, case):
+    KC.assert_small(KC.case_phi(rt, case))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_rhs(rt, case):
+    KC.assert_small(KC.case_rhs(rt, case))
+
+
+def test_diag_dense(rt):
+    KC.assert_small(KC.case_diag_dense(rt, "eq_small"))
+
+
+def test_gemm(rt):
+    KC.assert_small(KC.case_gemm(rt))

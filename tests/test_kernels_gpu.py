@@ -1,0 +1,56 @@
+"""GPU tier: product kernels through the C ABI on a B200 vs the oracle / reference fixtures."""
+import numpy as np
+import pytest
+
+import rt_util
+import kernel_cases as KC
+
+pytestmark = pytest.mark.gpu
+CASES = ["eq_small", "ineq_small", "eq_mid"]
+
+
+@pytest.fixture(scope="module")
+def rt():
+    return rt_util.cuda_runtime()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_block_matvec(rt, case):
+    KC.assert_small(KC.case_block_matvec(rt, case))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_phi(rt, case):
+    KC.assert_small(KC.case_phi(rt, case))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_rhs(rt, case):
+    KC.assert_small(KC.case_rhs(rt, case))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_diag_dense(rt, case):
+    KC.assert_small(KC.case_diag_dense(rt, case))
+
+
+def test_gemm(rt):
+    KC.assert_small(KC.case_gemm(rt))
+
+
+@pytest.mark.parametrize("r,R,s", [(55, 55, 5), (29, 44, 10), (64, 64, 8)])
+def test_block_matvec_large_vs_oracle(rt, r, R, s):
+    """Large-regime shapes (SURVEY 8a''): maxcut_13 r2 and graphm_3 r2 local blocks."""
+    import tt_oracle as O
+    from ttipm_b200 import kernels as K
+    rng = np.random.default_rng(r * 1000 + R)
+    keys = {(0, 0): (2, 2), (0, 1): (1, 1), (1, 2): (1, 1), (2, 1): (s, s - 1), (2, 2): (s - 1, s)}
+    A = {k: rng.standard_normal((a, 4, 4, b)) for k, (a, b) in keys.items()}
+    P1 = {k: rng.standard_normal((r, a, r)) for k, (a, b) in keys.items()}
+    P2 = {k: rng.standard_normal((R, b, R)) for k, (a, b) in keys.items()}
+    x = rng.standard_normal((r, 3, 4, R))
+    bm = O.BlockMatrix({k: [v] for k, v in A.items()}, transposes={(0, 1): (1, 0)})
+    want = O.block_local_product(bm, 0, P1, P2, x)
+    c = dict(A=A, transposes={(0, 1): (1, 0)}, aliases={})
+    y = K.block_matvec(KC.full_terms(rt, c, P1, P2, False, False), rt.to_device(x), 3, (r, R), rt=rt)
+    assert KC.rel(rt.to_host(y), want) < KC.TOL
