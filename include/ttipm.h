@@ -97,6 +97,25 @@ int ttipm_gemm(int M, int N, int K, double alpha, const double* A, int64_t a_rs,
                const double* B, int64_t b_rs, int64_t b_cs, int64_t b_bs, double beta, double* C, int64_t c_rs,
                int64_t c_cs, int64_t c_bs, int nbatch, void* stream);
 
+/* Device-resident LGMRES(restart, augment) on the Schur-reduced local KKT operator
+ *   eq   (ineq=0): [y; x]    -> [K00 y + K01 x ; K21 x - K22 (inv_I o K01^T y)]
+ *   ineq (ineq=1): [y; x; t] -> [K00 y + K01 x ; K21 x - K22 (inv_I o K01^T y + t) ; K31 x + K33 t]
+ * Replaces MatVecWrapper / IneqMatVecWrapper (reference cy_src/lgmres_cy.pyx:203-510) together with
+ * LGMRESSolver = PETSc KSP lgmres (reference src/tt_ipm.py:101-162; options at :249-254, :362-367):
+ * zero initial guess, no preconditioner, classical Gram-Schmidt, convergence ||r|| <= rtol*||rhs||,
+ * at most max_it inner steps.  Vectors are block-major (nblk, r, n, R) with nblk = 2 or 3.
+ * One persistent cooperative kernel runs the whole solve; `workspace` must hold at least
+ * ttipm_lgmres_workspace(...) doubles.  apply_only != 0 computes x = Op(rhs) instead (the matvec of
+ * the wrappers).  info (device, 6 doubles, may be NULL) = its, matvecs, reason, cycles, residual
+ * estimate, grid size; reason: 1 rtol, 2 atol, 3 max_it, -1 dtol, -2 breakdown, -3 null pivot, -4 nan.
+ * grid_hint = 0 lets the library choose the number of CTAs. */
+int64_t ttipm_lgmres_workspace(int ineq, int r, int R, int nmode, int restart, int augment);
+int ttipm_local_lgmres(int ineq, const ttipm_term* K00, const ttipm_term* K01, const ttipm_term* K21,
+                       const ttipm_term* K22, const ttipm_term* K31, const ttipm_term* K33, const double* inv_I,
+                       int r, int R, int nmode, const double* rhs, double* x, double* workspace, int64_t ws_doubles,
+                       int restart, int augment, int max_it, double rtol, int apply_only, int grid_hint,
+                       double* info, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #define TT_DEV __device__ __forceinline__
 #define TT_DEVFN __device__
+#define TT_DEVM __device__ __forceinline__
 #define TT_HD __host__ __device__ __forceinline__
 #define TT_GLOBAL __global__
 #define TT_SMEM_DECL(name) extern __shared__ __align__(16) unsigned char name[]

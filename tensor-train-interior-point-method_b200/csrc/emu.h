@@ -14,6 +14,7 @@
 
 #define TT_DEV static inline
 #define TT_DEVFN static
+#define TT_DEVM inline
 #define TT_HD static inline
 #define TT_GLOBAL static
 #define __launch_bounds__(...)

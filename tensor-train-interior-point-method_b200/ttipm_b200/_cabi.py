@@ -39,6 +39,10 @@ SIGNATURES = {
                                    C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ttipm_rhs_contract": (C.c_int, [C.POINTER(RhsTerm), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, i64,
                                      C.c_void_p]),
+    "ttipm_lgmres_workspace": (i64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ttipm_local_lgmres": (C.c_int, [C.c_int] + [C.POINTER(Term)] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, i64, C.c_int, C.c_int, C.c_int, C.c_double,
+                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ttipm_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, i64, i64, i64, C.c_void_p, i64, i64,
                              i64, C.c_double, C.c_void_p, i64, i64, i64, C.c_int, C.c_void_p]),
 }

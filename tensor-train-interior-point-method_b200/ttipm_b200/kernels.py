@@ -193,3 +193,59 @@ def gemm(A, B, out=None, alpha=1.0, beta=0.0, rt=None):
                              C3.stride(2), bs(C3), nb, rt.stream())
     rt.check(code, "ttipm_gemm")
     return out
+
+
+class ReducedOperator:
+    """Schur-reduced local KKT operator + device LGMRES (reference cy_src/lgmres_cy.pyx:203-510 and
+    src/tt_ipm.py:101-162).  P1/A/P2: dicts keyed by block (i, j) of device tensors."""
+
+    KEYS_EQ = [(0, 0), (0, 1), (2, 1), (2, 2)]
+    KEYS_INEQ = KEYS_EQ + [(3, 1), (3, 3)]
+
+    def __init__(self, P1, A, P2, inv_I, ineq, rt=None):
+        self.rt = rt or get_runtime()
+        self.ineq = bool(ineq)
+        self.inv_I = inv_I
+        assert inv_I.is_contiguous()
+        self.r, self.n, self.R = inv_I.shape
+        self.nblk = 3 if ineq else 2
+        self._keep = []
+        self._terms = []
+        for key in (self.KEYS_INEQ if ineq else self.KEYS_EQ):
+            tl = TermList().add(P1[key], A[key], P2[key], 0, 0)
+            arr, _ = tl.carray()
+            self._keep.append((tl, arr))
+            self._terms.append(arr)
+        while len(self._terms) < 6:
+            self._terms.append(None)
+        self._ws = None
+        self._ws_key = None
+
+    def _workspace(self, restart, augment):
+        key = (restart, augment)
+        if self._ws_key != key:
+            n = self.rt.lib.ttipm_lgmres_workspace(int(self.ineq), self.r, self.R, self.n, restart, augment)
+            self._ws = self.rt.empty(int(n))
+            self._ws_key = key
+        return self._ws
+
+    def _call(self, rhs, restart, augment, max_it, rtol, apply_only, grid_hint):
+        rt = self.rt
+        assert rhs.is_contiguous() and rhs.numel() == self.nblk * self.r * self.n * self.R
+        ws = self._workspace(restart, augment)
+        x = rt.empty(self.nblk, self.r, self.n, self.R)
+        info = rt.empty(6)
+        t = self._terms
+        code = rt.lib.ttipm_local_lgmres(int(self.ineq), t[0], t[1], t[2], t[3], t[4], t[5], _ptr(self.inv_I), self.r,
+                                         self.R, self.n, _ptr(rhs), _ptr(x), _ptr(ws), ws.numel(), restart, augment,
+                                         max_it, rtol, int(apply_only), grid_hint, _ptr(info), rt.stream())
+        rt.check(code, "ttipm_local_lgmres")
+        return x, info
+
+    def matvec(self, v, grid_hint=0):
+        """MatVecWrapper.matvec / IneqMatVecWrapper.matvec on a block-major device vector."""
+        return self._call(v, 4, 3, 1, 1e-5, True, grid_hint)[0]
+
+    def solve(self, rhs, restart, augment, max_it=300, rtol=1e-5, grid_hint=0):
+        """-> (x, info) ; info = device tensor [its, matvecs, reason, cycles, residual estimate, grid]."""
+        return self._call(rhs, restart, augment, max_it, rtol, False, grid_hint)

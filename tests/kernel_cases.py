@@ -140,3 +140,49 @@ def case_gemm(rt):
 def assert_small(errs, tol=TOL):
     bad = {k: v for k, v in errs.items() if not (v <= tol)}
     assert not bad, f"parity failures (rel err > {tol}): {bad}; all: {errs}"
+
+
+def _reduced_op(rt, c):
+    ineq = c["nb"] == 4
+    A, P1, P2 = _dev(rt, c["A"]), _dev(rt, c["P1"]), _dev(rt, c["P2"])
+    return K.ReducedOperator(P1, A, P2, rt.to_device(c["inv_I"]), ineq, rt=rt), ineq
+
+
+def case_reduced_matvec(rt, case, grid_hint=0):
+    """MatVecWrapper.matvec / IneqMatVecWrapper.matvec (reference cy_src/lgmres_cy.pyx:291-331, :490-510)."""
+    c = load_blp_case(case)
+    op, ineq = _reduced_op(rt, c)
+    y = op.matvec(rt.to_device(c["red_x"]), grid_hint=grid_hint)
+    return {"reduced_matvec": rel(rt.to_host(y).reshape(-1), c["red_y"])}
+
+
+def case_lgmres(rt, case, grid_hint=0, restart=None, shift=8.0, rtol=1e-5, max_it=300):
+    """Device LGMRES vs the oracle's PETSc-style LGMRES on the same (diagonally shifted) reduced operator:
+    same iteration count, same stopping reason, solution equal to rounding."""
+    import lgmres_ref
+    c = load_blp_case(case)
+    ineq = c["nb"] == 4
+    # make the random operator well conditioned: scale the diagonal blocks' interfaces
+    P1 = {k: v.copy() for k, v in c["P1"].items()}
+    for key in ((0, 0), (2, 1), (3, 3)):
+        if key in P1:
+            P1[key] = P1[key] + shift * np.stack([np.eye(P1[key].shape[0])] * P1[key].shape[1], axis=1)
+    cc = dict(c, P1=P1)
+    op, _ = _reduced_op(rt, cc)
+    oop = (O.ReducedOperatorIneq if ineq else O.ReducedOperatorEq)(P1, c["A"], c["P2"], c["inv_I"])
+    rng = np.random.default_rng(5)
+    nb = 3 if ineq else 2
+    r, n, R = c["inv_I"].shape
+    b = rng.standard_normal(nb * r * n * R)
+    m = r * n * R
+    restart = restart or min(m, 100)
+    aug = max(restart // 10, 3)
+    ref = lgmres_ref.lgmres(oop.matvec, b, rtol=rtol, max_it=max_it, restart=restart, augment=aug)
+    x, info = op.solve(rt.to_device(b), restart, aug, max_it=max_it, rtol=rtol, grid_hint=grid_hint)
+    info = rt.to_host(info)
+    xh = rt.to_host(x).reshape(-1)
+    code = {"rtol": 1, "atol": 2, "its": 3, "dtol": -1, "breakdown": -2, "null": -3, "nan": -4}[ref.reason]
+    errs = {"x": rel(xh, ref.x), "its": abs(info[0] - ref.its), "reason": abs(info[2] - code),
+            "true_res": max(0.0, float(np.linalg.norm(oop.matvec(xh) - b) / np.linalg.norm(b)) - 1.5 * rtol)
+            if ref.reason == "rtol" else 0.0}
+    return errs, dict(its=int(info[0]), ref_its=ref.its, reason=int(info[2]), grid=int(info[5]), cycles=int(info[3]))

@@ -34,3 +34,16 @@ def test_diag_dense(rt):
 
 def test_gemm(rt):
     KC.assert_small(KC.case_gemm(rt))
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("grid", [1, 2])
+def test_reduced_matvec(rt, case, grid):
+    KC.assert_small(KC.case_reduced_matvec(rt, case, grid_hint=grid))
+
+
+@pytest.mark.parametrize("case,grid,restart", [("eq_small", 1, None), ("eq_small", 2, 12), ("ineq_small", 2, 16)])
+def test_lgmres(rt, case, grid, restart):
+    errs, meta = KC.case_lgmres(rt, case, grid_hint=grid, restart=restart)
+    assert meta["its"] > 3, meta
+    KC.assert_small(errs, tol=1e-8)
