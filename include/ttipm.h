@@ -41,17 +41,21 @@ typedef struct ttipm_term {
     double alpha;
 } ttipm_term;
 
-/* K1 -- y[:, i] = sum over terms with out_block == i of alpha * (P1 A P2) x[:, in_block]
+/* K1 -- y[:, i] = y_scale * sum over terms with out_block == i of alpha * (P1 A P2) x[:, in_block]
+ *                   (+ sub_scale * sub[:, i] if sub != NULL)
  * Replaces TTBlockMatrixView.block_local_product / compressed_ / lcompressed_ / rcompressed_
  * (reference src/tt_als.py:190-238).  x block j element (rho, nu, Rho) lives at
- * x[batch*x_batch_stride + j*x_block_stride + rho*x_row_stride + nu*R + Rho]; y likewise with (l, L).
- * Output blocks without a term are zero-filled.  If `sub` != NULL the kernel stores y - sub
- * (sub has y's layout, no batch stride).  If `sumsq` != NULL it receives, per batch entry,
- * nb_out*L partial sums of squares of the stored values (sum them for the squared norm). */
+ * x[batch*x_batch_stride + j*x_block_stride + rho*x_row_stride + nu*x_mode_stride + Rho]; y likewise
+ * with (l, L) -- both the (r, b, n, R) block-core layout and the (r, n, b, R) forward unfolding of the
+ * sweep are expressible.  Output blocks without a term get y_scale*0 (+ sub).  sub has y's layout
+ * (no batch stride): with y_scale = 1, sub_scale = -1 the call returns the local residual A x - rhs.
+ * If `sumsq` != NULL it receives, per batch entry, nb_out*L partial sums of squares of the stored
+ * values (sum them for the squared norm). */
 int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, int L, int r, int R, int nmode, int nb_out,
-                       const double* x, int64_t x_block_stride, int64_t x_row_stride, int64_t x_batch_stride,
-                       double* y, int64_t y_block_stride, int64_t y_row_stride, int64_t y_batch_stride,
-                       const double* sub, double* sumsq, int nbatch, void* stream);
+                       const double* x, int64_t x_block_stride, int64_t x_row_stride, int64_t x_mode_stride,
+                       int64_t x_batch_stride, double* y, int64_t y_block_stride, int64_t y_row_stride,
+                       int64_t y_mode_stride, int64_t y_batch_stride, double y_scale, const double* sub,
+                       double sub_scale, double* sumsq, int nbatch, void* stream);
 
 /* K4 -- diag[l,m,L] = sum_s,S P1[l,s,l] A[s,m,m,S] P2[L,S,L]   (reference src/tt_ipm.py:191, :292);
  * if invert != 0 stores 1/diag (the inv_I of the Schur reduction). */
@@ -115,6 +119,39 @@ int ttipm_local_lgmres(int ineq, const ttipm_term* K00, const ttipm_term* K01, c
                        int r, int R, int nmode, const double* rhs, double* x, double* workspace, int64_t ws_doubles,
                        int restart, int augment, int max_it, double rtol, int apply_only, int grid_hint,
                        double* info, void* stream);
+
+/* ---- dense factorisations of core unfoldings (one CTA per matrix, batched) ---------------------- */
+/* Householder QR, A (M x N, strided) = Q (M x K) R (K x N), K = min(M, N); Q, R contiguous row-major.
+ * Replaces scipy.linalg.qr(mode="economic") at reference cy_src/tt_ops_cy.pyx:147, src/tt_als.py:358, :482.
+ * workspace: ttipm_qr_workspace() doubles (only touched when the matrix does not fit in shared memory). */
+int64_t ttipm_qr_workspace(int M, int N, int nbatch);
+int ttipm_qr(const double* A, int64_t a_rs, int64_t a_cs, int64_t a_bs, int M, int N, double* Q, double* R,
+             double* workspace, int nbatch, void* stream);
+
+/* "Left" SVD by one-sided Jacobi: A (M x N, strided) -> U (M x K), S (K, descending), Wt = S * V^T (K x N).
+ * Replaces scipy.linalg.svd at reference cy_src/tt_ops_cy.pyx:205,:291,:357,:404,:418 and
+ * src/tt_als.py:270,:331,:457 -- every call site there only consumes U, s and s*Vt.
+ * info (device int32 per batch entry, may be NULL) receives the number of Jacobi sweeps. */
+int64_t ttipm_svd_workspace(int M, int N, int nbatch);
+int ttipm_svd_left(const double* A, int64_t a_rs, int64_t a_cs, int64_t a_bs, int M, int N, double* U, double* S,
+                   double* Wt, double* workspace, int32_t* info, int nbatch, void* stream);
+
+/* ---- memory-bound helpers -------------------------------------------------------------------- */
+/* out = permute(in, perm) for a 4-D contiguous tensor (out axis k = in axis perm[k]); optionally every
+ * element is multiplied (scale_mode 1) or divided (2) by scale[index along OUTPUT axis scale_axis]
+ * (the per-block equilibration `scales` of reference src/tt_als.py:321-326, :369, :444-451, :496). */
+int ttipm_permute4(const double* in, const int32_t* in_dims, const int32_t* perm, double* out, const double* scale,
+                   int scale_axis, int scale_mode, void* stream);
+/* out[j] = max(||x[:, j, :]||_2, floor) for x (r, b, inner) contiguous (reference src/tt_als.py:321). */
+int ttipm_block_norms(const double* x, int r, int b, int inner, double floor_, double* out, void* stream);
+/* out = w .* (alpha a + beta b) + gamma c on (rows x inner) panels with row strides; b, c, w, out may be
+ * NULL; sumsq (256 doubles, may be NULL) receives partial sums of squares of the result. */
+int ttipm_ewise(int rows, int inner, double alpha, const double* a, int64_t a_rs, double beta, const double* b,
+                int64_t b_rs, double gamma, const double* c, int64_t c_rs, const double* w, int64_t w_rs, double* out,
+                int64_t out_rs, double* sumsq, void* stream);
+/* Residual norms of the rank-truncation loop (reference src/tt_als.py:338-345, :466-471) for all candidate
+ * ranks at once: out[j*256 + part] = partial || base - sum_{i>=j} Y_i ||^2, Y is (q x len). */
+int ttipm_trunc_resnorms(const double* base, const double* Y, int q, int64_t len, double* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -63,7 +63,7 @@ TT_DEV void lg_item(LgCtx& c, const MvTerm* terms, int nterms, int slot, int til
     for (int it = 0; it < nterms; ++it) {
         if (terms[it].out_blk != slot) continue;
         const double* xin = terms[it].in_blk == 3 ? p.tmp : src + (long)terms[it].in_blk * p.m;
-        mv_accumulate_term(terms[it], xin, g.nm * g.R, g, L0, Ltc, c.smem);
+        mv_accumulate_term(terms[it], xin, g.nm * g.R, g.R, g, L0, Ltc, c.smem);
     }
     const double* Ys = c.smem + g.oYs;
     const int cols = g.nm * Ltc;

@@ -9,9 +9,10 @@ struct MvParams {
     int nterms;
     MvTerm t[TTIPM_MAX_TERMS];
     const double* x;
-    long x_bs, x_rs, x_batch;
+    long x_bs, x_rs, x_ns, x_batch;
     double* y;
-    long y_bs, y_rs, y_batch;
+    long y_bs, y_rs, y_ns, y_batch;
+    double y_scale, sub_scale;
     const double* sub;
     double* sumsq;
     int nb_out;
@@ -28,7 +29,7 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_block_matvec(const MvParams p
     const double* xb = p.x + (long)batch * p.x_batch;
     for (int it = 0; it < p.nterms; ++it) {
         if (p.t[it].out_blk != out_blk) continue;
-        mv_accumulate_term(p.t[it], xb + (long)p.t[it].in_blk * p.x_bs, (int)p.x_rs, g, L0, Ltc, smem);
+        mv_accumulate_term(p.t[it], xb + (long)p.t[it].in_blk * p.x_bs, (int)p.x_rs, (int)p.x_ns, g, L0, Ltc, smem);
     }
     // epilogue: Ys[lam, (mu, lt)] -> y[out_blk][lam, mu, L0 + lt]
     const double* Ys = smem + g.oYs;
@@ -38,9 +39,9 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_block_matvec(const MvParams p
     const int cols = g.nm * Ltc;
     for (int i = threadIdx.x; i < g.l * cols; i += blockDim.x) {
         const int lam = i / cols, c = i % cols, mu = c / Ltc, lt = c % Ltc;
-        const long o = (long)lam * p.y_rs + mu * g.L + L0 + lt;
-        double v = Ys[lam * g.ldY + mu * Ltc + lt];
-        if (sb) v -= sb[o];
+        const long o = (long)lam * p.y_rs + mu * p.y_ns + L0 + lt;
+        double v = p.y_scale * Ys[lam * g.ldY + mu * Ltc + lt];
+        if (sb) v += p.sub_scale * sb[o];
         yb[o] = v;
         ss += v * v;
     }
@@ -115,9 +116,9 @@ using namespace ttipm;
 
 extern "C" int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, int L, int r, int R, int nmode,
                                   int nb_out, const double* x, int64_t x_block_stride, int64_t x_row_stride,
-                                  int64_t x_batch_stride, double* y, int64_t y_block_stride, int64_t y_row_stride,
-                                  int64_t y_batch_stride, const double* sub, double* sumsq, int nbatch,
-                                  void* stream) {
+                                  int64_t x_mode_stride, int64_t x_batch_stride, double* y, int64_t y_block_stride,
+                                  int64_t y_row_stride, int64_t y_mode_stride, int64_t y_batch_stride, double y_scale,
+                                  const double* sub, double sub_scale, double* sumsq, int nbatch, void* stream) {
     if (nterms < 0 || nterms > TTIPM_MAX_TERMS) return fail(1, "block_matvec: nterms=%d out of range", nterms);
     if (l < 1 || L < 1 || r < 1 || R < 1 || nmode < 1 || nb_out < 1 || nbatch < 1)
         return fail(1, "block_matvec: bad dims l=%d L=%d r=%d R=%d n=%d nb=%d batch=%d", l, L, r, R, nmode, nb_out, nbatch);
@@ -135,8 +136,10 @@ extern "C" int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, in
     if (mv_plan(p.g, l, L, r, R, nmode, smax, Smax, nb_out, (di.sms * 2 + nbatch - 1) / nbatch, di.smem_optin))
         return fail(4, "block_matvec: shape l=%d L=%d r=%d R=%d s=%d S=%d needs %d B shared memory (> %d)", l, L, r,
                     R, smax, Smax, p.g.smem_bytes, di.smem_optin);
-    p.x = x; p.x_bs = x_block_stride; p.x_rs = x_row_stride; p.x_batch = x_batch_stride;
-    p.y = y; p.y_bs = y_block_stride; p.y_rs = y_row_stride; p.y_batch = y_batch_stride;
+    p.x = x; p.x_bs = x_block_stride; p.x_rs = x_row_stride; p.x_ns = x_mode_stride; p.x_batch = x_batch_stride;
+    p.y = y; p.y_bs = y_block_stride; p.y_rs = y_row_stride; p.y_ns = y_mode_stride; p.y_batch = y_batch_stride;
+    p.y_scale = y_scale; p.sub_scale = sub_scale;
+    if (!fits_int(x_row_stride) || !fits_int(x_mode_stride)) return fail(1, "block_matvec: x strides too large");
     p.sub = sub; p.sumsq = sumsq; p.nb_out = nb_out;
     tt_stream_t st = (tt_stream_t)stream;
     if (sumsq && dev_memset(sumsq, 0, sizeof(double) * (size_t)nbatch * nb_out * L, st)) return fail(5, "memset failed");

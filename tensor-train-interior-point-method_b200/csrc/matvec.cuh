@@ -73,8 +73,8 @@ static inline int mv_plan(MvGeom& g, int l, int L, int r, int R, int nm, int sma
 
 #if defined(__CUDACC__) || defined(TTIPM_EMU)
 // Accumulate alpha * (term applied to x_blk) for L-tile [L0, L0+Ltc) into Ys (l x ldY, column (m, Lt)).
-//   x_blk: element (rho, nu, Rho) at x_blk[rho * x_rs + nu * R + Rho]
-TT_DEV void mv_accumulate_term(const MvTerm& t, const double* __restrict__ x_blk, int x_rs, const MvGeom& g,
+//   x_blk: element (rho, nu, Rho) at x_blk[rho * x_rs + nu * x_ns + Rho]
+TT_DEV void mv_accumulate_term(const MvTerm& t, const double* __restrict__ x_blk, int x_rs, int x_ns, const MvGeom& g,
                                int L0, int Ltc, double* smem) {
     double* T1 = smem + g.oT1;
     double* T2 = smem + g.oT2;
@@ -91,7 +91,7 @@ TT_DEV void mv_accumulate_term(const MvTerm& t, const double* __restrict__ x_blk
         As[row * ldA + col] = t.A[sg * t.as_[0] + mu * t.as_[1] + nu * t.as_[2] + sp * t.as_[3]];
     }
     // stage 1: T1[(rho, Lt), (nu, sig')] = sum_Rho x[(rho, nu), Rho] * P2[(L0 + Lt, sig'), Rho]
-    tgemm(r * nm, Ltc * S, R, x_blk, ax2(nm, x_rs, R), ax1(1),
+    tgemm(r * nm, Ltc * S, R, x_blk, ax2(nm, x_rs, x_ns), ax1(1),
           t.P2 + (long)L0 * t.p2s[0], ax1(t.p2s[2]), ax2(S, t.p2s[0], t.p2s[1]),
           [&](int m, int n, double v) {
               const int rho = m / nm, nu = m % nm, lt = n / S, sp = n % S;

@@ -30,8 +30,8 @@ SIGNATURES = {
     "ttipm_last_error": (C.c_char_p, []),
     "ttipm_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ttipm_block_matvec": (C.c_int, [C.POINTER(Term), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                     C.c_void_p, i64, i64, i64, C.c_void_p, i64, i64, i64, C.c_void_p, C.c_void_p,
-                                     C.c_int, C.c_void_p]),
+                                     C.c_void_p, i64, i64, i64, i64, C.c_void_p, i64, i64, i64, i64, C.c_double,
+                                     C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p]),
     "ttipm_local_diag": (C.c_int, [C.POINTER(Term), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ttipm_local_dense": (C.c_int, [C.POINTER(Term), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                     C.c_void_p]),
@@ -43,6 +43,18 @@ SIGNATURES = {
     "ttipm_local_lgmres": (C.c_int, [C.c_int] + [C.POINTER(Term)] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, i64, C.c_int, C.c_int, C.c_int, C.c_double,
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ttipm_qr_workspace": (i64, [C.c_int, C.c_int, C.c_int]),
+    "ttipm_qr": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                           C.c_void_p]),
+    "ttipm_svd_workspace": (i64, [C.c_int, C.c_int, C.c_int]),
+    "ttipm_svd_left": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ttipm_permute4": (C.c_int, [C.c_void_p, C.POINTER(i32), C.POINTER(i32), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p]),
+    "ttipm_block_norms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    "ttipm_ewise": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_void_p, i64, C.c_double, C.c_void_p, i64, C.c_double,
+                              C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p]),
+    "ttipm_trunc_resnorms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, i64, C.c_void_p, C.c_void_p]),
     "ttipm_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, i64, i64, i64, C.c_void_p, i64, i64,
                              i64, C.c_double, C.c_void_p, i64, i64, i64, C.c_int, C.c_void_p]),
 }

@@ -44,16 +44,24 @@ class TermList:
         return arr, n
 
 
-def block_matvec(terms, x, nb_out, out_ranks, sub=None, want_norm=False, rt=None):
-    """y[:, i] = sum_terms alpha * (P1 A P2) x[:, in_block]   (reference src/tt_als.py:190-238).
+def block_matvec(terms, x, nb_out, out_ranks, sub=None, y_scale=1.0, sub_scale=-1.0, want_norm=False,
+                 x_layout="rbnR", rt=None):
+    """y[:, i] = y_scale * sum_terms alpha * (P1 A P2) x[:, in_block] (+ sub_scale * sub[:, i])
+    (reference src/tt_als.py:190-238).
 
-    x: (r, b_in, n, R) or batched (B, r, b_in, n, R); returns y (l, nb_out, n, L) [batched likewise]
-    and, if want_norm, a device tensor with the squared norm partials (sum them on the host)."""
+    x: (r, b_in, n, R) ["rbnR"] or the forward unfolding (r, n, b_in, R) ["rnbR"], optionally with a
+    leading batch axis; returns y (l, nb_out, n, L) [batched likewise] and, if want_norm, a device
+    tensor with the squared-norm partials (sum them on the host)."""
     rt = rt or get_runtime()
     batched = x.dim() == 5
     xb = x if batched else x.unsqueeze(0)
-    B, r, b_in, n, R = xb.shape
-    assert xb.stride(4) == 1 and xb.stride(3) == R, "x needs contiguous (n, R) panels"
+    if x_layout == "rbnR":
+        B, r, b_in, n, R = xb.shape
+        x_bs, x_rs, x_ns = xb.stride(2), xb.stride(1), xb.stride(3)
+    else:
+        B, r, n, b_in, R = xb.shape
+        x_bs, x_rs, x_ns = xb.stride(3), xb.stride(1), xb.stride(2)
+    assert xb.stride(4) == 1, "x needs a unit stride along R"
     l, L = out_ranks
     y = rt.empty(B, l, nb_out, n, L)
     arr, nt = terms.carray()
@@ -64,9 +72,9 @@ def block_matvec(terms, x, nb_out, out_ranks, sub=None, want_norm=False, rt=None
     sumsq = rt.empty(B, nb_out * L) if want_norm else None
     if sub is not None:
         assert sub.shape == (l, nb_out, n, L) and sub.is_contiguous()
-    code = rt.lib.ttipm_block_matvec(arr, nt, l, L, r, R, n, nb_out, _ptr(xb), xb.stride(2), xb.stride(1),
-                                     xb.stride(0), _ptr(y), y.stride(2), y.stride(1), y.stride(0), _ptr(sub),
-                                     _ptr(sumsq), B, rt.stream())
+    code = rt.lib.ttipm_block_matvec(arr, nt, l, L, r, R, n, nb_out, _ptr(xb), x_bs, x_rs, x_ns, xb.stride(0),
+                                     _ptr(y), y.stride(2), y.stride(1), y.stride(3), y.stride(0), y_scale,
+                                     _ptr(sub), sub_scale, _ptr(sumsq), B, rt.stream())
     rt.check(code, "ttipm_block_matvec")
     if not batched:
         y = y[0]
@@ -249,3 +257,115 @@ class ReducedOperator:
     def solve(self, rhs, restart, augment, max_it=300, rtol=1e-5, grid_hint=0):
         """-> (x, info) ; info = device tensor [its, matvecs, reason, cycles, residual estimate, grid]."""
         return self._call(rhs, restart, augment, max_it, rtol, False, grid_hint)
+
+
+# ---- dense factorisations -------------------------------------------------------------------------
+def _mat3(A):
+    return A if A.dim() == 3 else A.unsqueeze(0)
+
+
+def qr(A, rt=None):
+    """Economic QR of a strided 2-D view (or a batch): returns Q (M, K), R (K, N)."""
+    rt = rt or get_runtime()
+    A3 = _mat3(A)
+    nb, M, N = A3.shape
+    Kk = min(M, N)
+    Q, R = rt.empty(nb, M, Kk), rt.empty(nb, Kk, N)
+    ws = rt.empty(int(rt.lib.ttipm_qr_workspace(M, N, nb)))
+    code = rt.lib.ttipm_qr(_ptr(A3), A3.stride(1), A3.stride(2), A3.stride(0) if nb > 1 else 0, M, N, _ptr(Q), _ptr(R),
+                           _ptr(ws), nb, rt.stream())
+    rt.check(code, "ttipm_qr")
+    return (Q, R) if A.dim() == 3 else (Q[0], R[0])
+
+
+def svd_left(A, rt=None):
+    """U (M, K), s (K) descending, W = diag(s) V^T (K, N) of a strided 2-D view (or a batch)."""
+    rt = rt or get_runtime()
+    A3 = _mat3(A)
+    nb, M, N = A3.shape
+    Kk = min(M, N)
+    U, S, W = rt.empty(nb, M, Kk), rt.empty(nb, Kk), rt.empty(nb, Kk, N)
+    ws = rt.empty(int(rt.lib.ttipm_svd_workspace(M, N, nb)))
+    code = rt.lib.ttipm_svd_left(_ptr(A3), A3.stride(1), A3.stride(2), A3.stride(0) if nb > 1 else 0, M, N, _ptr(U),
+                                 _ptr(S), _ptr(W), _ptr(ws), C.c_void_p(0), nb, rt.stream())
+    rt.check(code, "ttipm_svd_left")
+    return (U, S, W) if A.dim() == 3 else (U[0], S[0], W[0])
+
+
+# ---- memory-bound helpers ---------------------------------------------------------------------------
+def permute4(x, perm, scale=None, scale_axis=0, divide=False, rt=None):
+    """out = x.permute(perm) materialised (x 4-D contiguous), optionally scaled along an OUTPUT axis."""
+    rt = rt or get_runtime()
+    assert x.dim() == 4 and x.is_contiguous()
+    dims = (_cabi.i32 * 4)(*x.shape)
+    pm = (_cabi.i32 * 4)(*perm)
+    out = rt.empty(*[x.shape[q] for q in perm])
+    if scale is not None:
+        assert scale.is_contiguous() and scale.numel() == out.shape[scale_axis]
+    code = rt.lib.ttipm_permute4(_ptr(x), dims, pm, _ptr(out), _ptr(scale), scale_axis, 2 if divide else 1,
+                                 rt.stream())
+    rt.check(code, "ttipm_permute4")
+    return out
+
+
+def block_norms(x, floor=1e-10, rt=None):
+    """scales[j] = max(||x[:, j]||, floor) for x (r, b, n, R) contiguous (reference src/tt_als.py:321)."""
+    rt = rt or get_runtime()
+    assert x.is_contiguous()
+    r, b = x.shape[0], x.shape[1]
+    out = rt.empty(b)
+    rt.check(rt.lib.ttipm_block_norms(_ptr(x), r, b, x.numel() // (r * b), floor, _ptr(out), rt.stream()),
+             "ttipm_block_norms")
+    return out
+
+
+def _panels(tensors):
+    """Common (rows, inner) panel view of equally shaped tensors that are contiguous or x[:, j]-style slices;
+    returns rows, inner and the row stride of every tensor (0 for None)."""
+    live = [t for t in tensors if t is not None]
+    shape = live[0].shape
+    for t in live:
+        assert t.shape == shape, (t.shape, shape)
+    if all(t.is_contiguous() for t in live):
+        n = live[0].numel()
+        return 1, n, [n if t is not None else 0 for t in tensors]
+    rows = shape[0]
+    inner = 1
+    for q in shape[1:]:
+        inner *= q
+    strides = []
+    for t in tensors:
+        if t is None:
+            strides.append(0)
+            continue
+        acc = 1
+        for q in range(t.dim() - 1, 0, -1):
+            assert t.shape[q] == 1 or t.stride(q) == acc, "unsupported view"
+            acc *= t.shape[q]
+        strides.append(t.stride(0))
+    return rows, inner, strides
+
+
+def ewise(a, alpha=1.0, b=None, beta=0.0, c=None, gamma=0.0, w=None, out=None, want_sumsq=False, store=True, rt=None):
+    """out = w .* (alpha a + beta b) + gamma c on equally shaped tensors (contiguous or [:, j]-style slices)."""
+    rt = rt or get_runtime()
+    if out is None and store:
+        out = rt.empty(*a.shape)
+    rows, inner, (a_rs, b_rs, c_rs, w_rs, o_rs) = _panels([a, b, c, w, out])
+    ss = rt.empty(256) if want_sumsq else None
+    code = rt.lib.ttipm_ewise(rows, inner, alpha, _ptr(a), a_rs, beta, _ptr(b), b_rs, gamma, _ptr(c), c_rs, _ptr(w),
+                              w_rs, _ptr(out), o_rs, _ptr(ss), rt.stream())
+    rt.check(code, "ttipm_ewise")
+    return (out, ss) if want_sumsq else out
+
+
+def trunc_resnorms(base, Y, rt=None):
+    """partials (q, 256) of || base - sum_{i>=j} Y_i ||^2 (reference src/tt_als.py:338-345)."""
+    rt = rt or get_runtime()
+    assert base.is_contiguous() and Y.is_contiguous()
+    q = Y.shape[0]
+    ln = base.numel()
+    assert Y.numel() == q * ln
+    out = rt.empty(q, 256)
+    rt.check(rt.lib.ttipm_trunc_resnorms(_ptr(base), _ptr(Y), q, ln, _ptr(out), rt.stream()), "ttipm_trunc_resnorms")
+    return out

@@ -186,3 +186,65 @@ def case_lgmres(rt, case, grid_hint=0, restart=None, shift=8.0, rtol=1e-5, max_i
             "true_res": max(0.0, float(np.linalg.norm(oop.matvec(xh) - b) / np.linalg.norm(b)) - 1.5 * rtol)
             if ref.reason == "rtol" else 0.0}
     return errs, dict(its=int(info[0]), ref_its=ref.its, reason=int(info[2]), grid=int(info[5]), cycles=int(info[3]))
+
+
+def case_qr_svd(rt, shapes=((7, 5), (5, 7), (6, 6), (12, 3), (3, 12), (1, 4), (4, 1), (20, 12))):
+    """QR / left-SVD parity (gauge-aware): reconstruction, orthogonality, singular values."""
+    import scipy.linalg as sla
+    rng = np.random.default_rng(11)
+    errs = {}
+    for (M, N) in shapes:
+        a = rng.standard_normal((M, N))
+        if M >= 6 and N >= 5:
+            a[:, -1] = a[:, 0] * 2.0            # exactly rank deficient: zero singular value
+        Kk = min(M, N)
+        at = rt.to_device(a.T.copy()).t()       # strided input view
+        Q, R = (rt.to_host(t) for t in K.qr(at, rt=rt))
+        errs[f"qr_rec{M}x{N}"] = rel(Q @ R, a)
+        errs[f"qr_orth{M}x{N}"] = float(np.linalg.norm(Q.T @ Q - np.eye(Kk)))
+        errs[f"qr_tri{M}x{N}"] = float(np.linalg.norm(np.tril(R, -1)))
+        U, S, W = (rt.to_host(t) for t in K.svd_left(at, rt=rt))
+        sref = sla.svd(a, compute_uv=False)
+        errs[f"svd_s{M}x{N}"] = float(np.max(np.abs(S - sref)) / sref[0])
+        errs[f"svd_rec{M}x{N}"] = rel(U @ W, a)
+        errs[f"svd_orth{M}x{N}"] = float(np.linalg.norm(U.T @ U - np.eye(Kk)))
+        errs[f"svd_w{M}x{N}"] = float(np.max(np.abs(np.linalg.norm(W, axis=1) - S)) / sref[0])
+    ab = rng.standard_normal((3, 6, 4))
+    U, S, W = (rt.to_host(t) for t in K.svd_left(rt.to_device(ab), rt=rt))
+    errs["svd_batched"] = rel(np.einsum("bik,bkj->bij", U, W), ab)
+    return errs
+
+
+def case_elementwise(rt):
+    rng = np.random.default_rng(12)
+    errs = {}
+    x = rng.standard_normal((5, 3, 4, 6))
+    xd = rt.to_device(x)
+    sc = K.block_norms(xd, rt=rt)
+    want = np.maximum(np.array([np.linalg.norm(x[:, j]) for j in range(3)]), 1e-10)
+    errs["block_norms"] = rel(rt.to_host(sc), want)
+    errs["perm_mul"] = rel(rt.to_host(K.permute4(xd, (0, 2, 1, 3), scale=sc, scale_axis=2, rt=rt)),
+                           (x * want.reshape(1, 3, 1, 1)).transpose(0, 2, 1, 3))
+    errs["perm_div"] = rel(rt.to_host(K.permute4(xd, (3, 1, 0, 2), scale=sc, scale_axis=1, divide=True, rt=rt)),
+                           (x / want.reshape(1, 3, 1, 1)).transpose(3, 1, 0, 2))
+    errs["perm_plain"] = rel(rt.to_host(K.permute4(xd, (1, 0, 3, 2), rt=rt)), x.transpose(1, 0, 3, 2))
+    a, b, c, w = (rng.standard_normal((5, 4, 6)) for _ in range(4))
+    o, ss = K.ewise(rt.to_device(a), 2.0, rt.to_device(b), -1.0, rt.to_device(c), 0.5, rt.to_device(w),
+                    want_sumsq=True, rt=rt)
+    ref = w * (2 * a - b) + 0.5 * c
+    errs["ewise"] = rel(rt.to_host(o), ref)
+    errs["ewise_ss"] = rel(rt.to_host(ss).sum(), (ref ** 2).sum())
+    # sliced operands: rhs[:, 1] style views
+    o = K.ewise(xd[:, 1], 1.0, b=rt.to_device(a), beta=-1.0, w=rt.to_device(w), rt=rt)
+    errs["ewise_slice"] = rel(rt.to_host(o), w * (x[:, 1] - a))
+    dst = rt.to_device(x)
+    K.ewise(rt.to_device(a), 3.0, out=dst[:, 2], rt=rt)
+    xx = x.copy()
+    xx[:, 2] = 3 * a
+    errs["ewise_out_slice"] = rel(rt.to_host(dst), xx)
+    base = rng.standard_normal(700)
+    Y = rng.standard_normal((5, 700))
+    part = rt.to_host(K.trunc_resnorms(rt.to_device(base), rt.to_device(Y), rt=rt)).sum(axis=1)
+    want = np.array([np.sum((base - Y[j:].sum(axis=0)) ** 2) for j in range(5)])
+    errs["trunc_resnorms"] = rel(part, want)
+    return errs

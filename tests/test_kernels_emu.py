@@ -47,3 +47,11 @@ def test_lgmres(rt, case, grid, restart):
     errs, meta = KC.case_lgmres(rt, case, grid_hint=grid, restart=restart)
     assert meta["its"] > 3, meta
     KC.assert_small(errs, tol=1e-8)
+
+
+def test_qr_svd(rt):
+    KC.assert_small(KC.case_qr_svd(rt), tol=1e-12)
+
+
+def test_elementwise(rt):
+    KC.assert_small(KC.case_elementwise(rt), tol=1e-13)

@@ -54,3 +54,27 @@ def test_block_matvec_large_vs_oracle(rt, r, R, s):
     c = dict(A=A, transposes={(0, 1): (1, 0)}, aliases={})
     y = K.block_matvec(KC.full_terms(rt, c, P1, P2, False, False), rt.to_device(x), 3, (r, R), rt=rt)
     assert KC.rel(rt.to_host(y), want) < KC.TOL
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("grid", [0, 1, 7])
+def test_reduced_matvec(rt, case, grid):
+    KC.assert_small(KC.case_reduced_matvec(rt, case, grid_hint=grid))
+
+
+@pytest.mark.parametrize("case,grid,restart,shift", [("eq_small", 1, None, 8.0), ("eq_small", 4, 12, 8.0),
+                                                     ("ineq_small", 3, 16, 8.0), ("eq_mid", 0, None, 20.0),
+                                                     ("eq_mid", 16, 30, 20.0), ("eq_mid", 148, None, 20.0)])
+def test_lgmres(rt, case, grid, restart, shift):
+    errs, meta = KC.case_lgmres(rt, case, grid_hint=grid, restart=restart, shift=shift)
+    print(meta)
+    KC.assert_small(errs, tol=1e-8)
+
+
+def test_qr_svd(rt):
+    KC.assert_small(KC.case_qr_svd(rt, shapes=((7, 5), (5, 7), (6, 6), (12, 3), (3, 12), (1, 4), (4, 1), (20, 12),
+                                               (88, 66), (220, 165), (165, 220), (40, 300))), tol=1e-11)
+
+
+def test_elementwise(rt):
+    KC.assert_small(KC.case_elementwise(rt), tol=1e-13)
