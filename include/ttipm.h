@@ -153,6 +153,21 @@ int ttipm_ewise(int rows, int inner, double alpha, const double* a, int64_t a_rs
  * ranks at once: out[j*256 + part] = partial || base - sum_{i>=j} Y_i ||^2, Y is (q x len). */
 int ttipm_trunc_resnorms(const double* base, const double* Y, int q, int64_t len, double* out, void* stream);
 
+/* ---- TT primitives of the IPM driver (memory bound) ---------------------------------------------- */
+/* One core of tt_add (reference cy_src/tt_ops_cy.pyx:229-258): mode 0 = first core (concatenate on the
+ * last axis), 1 = middle core (block diagonal), 2 = last core (concatenate on the first axis);
+ * a is (ra, n, Ra), b is (rb, n, Rb), n = product of the mode sizes. */
+int ttipm_block_diag(const double* a, const double* b, double* out, int ra, int Ra, int rb, int Rb, int n, int mode,
+                     void* stream);
+/* Embeddings of reference src/tt_ops.py:360-375 and :312-316: mode 0 = I (x) M, 1 = M (x) I
+ * (in (r,2,2,R) -> out (r,4,4,R)); mode 2 = diagonal embedding (in (r,q,R) -> out (r,q,q,R)). */
+int ttipm_embed(const double* in, double* out, int r, int R, int q, int mode, void* stream);
+/* out (rows x cols, contiguous) = in (strided) scaled along axis 0 (rows) or 1 (columns) by s; divide != 0
+ * divides instead (entries with s == 0 are left unscaled).  Used to move singular values between the
+ * two factors of the zip-up products (reference cy_src/tt_ops_cy.pyx:407-409, :421-424). */
+int ttipm_scale2d(const double* in, int64_t in_rs, int64_t in_cs, int rows, int cols, const double* s, int axis,
+                  int divide, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,11 @@ SIGNATURES = {
     "ttipm_ewise": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_void_p, i64, C.c_double, C.c_void_p, i64, C.c_double,
                               C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p]),
     "ttipm_trunc_resnorms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, i64, C.c_void_p, C.c_void_p]),
+    "ttipm_block_diag": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_void_p]),
+    "ttipm_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ttipm_scale2d": (C.c_int, [C.c_void_p, i64, i64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                C.c_void_p]),
     "ttipm_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, i64, i64, i64, C.c_void_p, i64, i64,
                              i64, C.c_double, C.c_void_p, i64, i64, i64, C.c_int, C.c_void_p]),
 }

@@ -369,3 +369,59 @@ def trunc_resnorms(base, Y, rt=None):
     out = rt.empty(q, 256)
     rt.check(rt.lib.ttipm_trunc_resnorms(_ptr(base), _ptr(Y), q, ln, _ptr(out), rt.stream()), "ttipm_trunc_resnorms")
     return out
+
+
+# ---- TT primitives --------------------------------------------------------------------------------
+def block_diag(a, b, where, rt=None):
+    """One core of tt_add (reference cy_src/tt_ops_cy.pyx:229-258); where in {'first','mid','last'}."""
+    rt = rt or get_runtime()
+    a, b = a.contiguous(), b.contiguous()
+    mode = {"first": 0, "mid": 1, "last": 2}[where]
+    ra, Ra, rb, Rb = a.shape[0], a.shape[-1], b.shape[0], b.shape[-1]
+    mid = tuple(a.shape[1:-1])
+    assert mid == tuple(b.shape[1:-1])
+    n = 1
+    for q in mid:
+        n *= q
+    ro = ra if mode == 0 else ra + rb
+    Ro = Ra if mode == 2 else Ra + Rb
+    out = rt.empty(ro, *mid, Ro)
+    rt.check(rt.lib.ttipm_block_diag(_ptr(a), _ptr(b), _ptr(out), ra, Ra, rb, Rb, n, mode, rt.stream()),
+             "ttipm_block_diag")
+    return out
+
+
+def embed(core, kind, rt=None):
+    """'IkronM' / 'MkronI' on a (r,2,2,R) core -> (r,4,4,R); 'diag' on a (r,q,R) core -> (r,q,q,R)
+    (reference src/tt_ops.py:360-375, :312-316)."""
+    rt = rt or get_runtime()
+    core = core.contiguous()
+    mode = {"IkronM": 0, "MkronI": 1, "diag": 2}[kind]
+    r, R = core.shape[0], core.shape[-1]
+    if mode == 2:
+        q = core.shape[1]
+        out = rt.empty(r, q, q, R)
+    else:
+        assert tuple(core.shape[1:3]) == (2, 2)
+        q = 4
+        out = rt.empty(r, 4, 4, R)
+    rt.check(rt.lib.ttipm_embed(_ptr(core), _ptr(out), r, R, q, mode, rt.stream()), "ttipm_embed")
+    return out
+
+
+def _scale2d(M, s, axis, divide, rt):
+    rt = rt or get_runtime()
+    rows, cols = M.shape
+    out = rt.empty(rows, cols)
+    s = s.contiguous()
+    rt.check(rt.lib.ttipm_scale2d(_ptr(M), M.stride(0), M.stride(1), rows, cols, _ptr(s), axis, int(divide),
+                                  _ptr(out), rt.stream()), "ttipm_scale2d")
+    return out
+
+
+def scale_cols(M, s, divide=False, rt=None):
+    return _scale2d(M, s, 1, divide, rt)
+
+
+def scale_rows(M, s, divide=False, rt=None):
+    return _scale2d(M, s, 0, divide, rt)

@@ -1,22 +1,452 @@
-"""TT algebra of the IPM driver on the device (placeholder header, filled in below)."""
+"""TT algebra of the IPM driver on the device.
+
+Same functions, argument meaning and mutation behaviour as the reference's cy_src/tt_ops_cy.pyx and
+the IPM-used subset of src/tt_ops.py; inputs and outputs are lists of NumPy cores (the reference's
+boundary type), the arithmetic runs in the kernels of libttipm_b200 (gemm / QR / Jacobi SVD /
+block-diagonal assembly / embeddings).  Rank decisions are taken on the host from the
+device-computed singular values with the reference's exact rule (prune_singular_vals).
+
+Functions ending in `_dev` take and return lists of device tensors, so composite operations keep
+their intermediates in HBM; the NumPy-boundary wrappers upload once and download once.
+"""
+import math
+
 import numpy as np
 
+from . import kernels as K
+from .runtime import get_runtime
 
-def tt_inner_prod_host(a, b):
-    res = np.ones((1, 1))
-    for c1, c2 in zip(a, b):
-        t = np.tensordot(res, c1, axes=([0], [0]))
-        ax = list(range(c1.ndim - 1))
-        res = np.tensordot(t, c2, axes=(ax, ax))
-    return float(res[0, 0])
+
+# ---- pure bookkeeping (no arithmetic): kept on the host exactly as in the reference ---------------
+def tt_ranks(tt):
+    """cy_src/tt_ops_cy.pyx:82-92."""
+    return [c.shape[0] for c in tt[1:]]
+
+
+def tt_identity(dim):
+    """cy_src/tt_ops_cy.pyx:21-29 (d references to ONE array, like the reference)."""
+    I = np.eye(2).reshape(1, 2, 2, 1)
+    return [I] * dim
+
+
+def tt_zero_matrix(dim):
+    """cy_src/tt_ops_cy.pyx:33-41."""
+    Z = np.zeros((1, 2, 2, 1))
+    return [Z] * dim
+
+
+def tt_one_matrix(dim):
+    """cy_src/tt_ops_cy.pyx:45-53."""
+    W = np.ones((1, 2, 2, 1))
+    return [W] * dim
+
+
+def tt_transpose(tt):
+    """cy_src/tt_ops_cy.pyx:57-78 (views; axes 1,2 swapped from the first 4-D core onward)."""
+    split = int(np.argmax([np.ndim(c) for c in tt]))
+    return list(tt[:split]) + [np.swapaxes(c, 1, 2) for c in tt[split:]]
+
+
+def tt_swap_all(tt):
+    """cy_src/tt_ops_cy.pyx:118-128."""
+    return [np.swapaxes(c, 0, -1) for c in reversed(tt)]
+
+
+def tt_reshape(tt, shape):
+    """src/tt_ops.py:330-333 (the core-merging branch is unused by the IPM path)."""
+    if np.prod(shape) > np.prod(tt[0].shape[1:-1]):
+        raise NotImplementedError("tt_reshape with core merging (src/tt_ops.py:335-339) is off the IPM path")
+    return [c.reshape(c.shape[0], *shape, c.shape[-1]) for c in tt]
 
 
 def tt_scale(alpha, tt):
+    """cy_src/tt_ops_cy.pyx:96-114: the C signature rounds alpha to float32 and ONE core, drawn with
+    np.random.randint (advancing the global RNG), is scaled; all other cores are shared."""
     idx = np.random.randint(0, len(tt))
     out = list(tt)
-    out[idx] = float(np.float32(alpha)) * tt[idx]
+    a32 = float(np.float32(alpha))
+    rt = get_runtime()
+    core = rt.to_device(tt[idx])
+    out[idx] = rt.to_host(K.ewise(core, a32, rt=rt)).reshape(tt[idx].shape)
     return out
 
 
-def tt_normalise(tt, radius=1):
-    return tt_scale(np.divide(int(radius), np.sqrt(tt_inner_prod_host(tt, tt))), tt)
+def prune_singular_vals(s, eps):
+    """cy_src/tt_ops_cy.pyx:162-177."""
+    s = np.asarray(s, dtype=np.float64)
+    if np.linalg.norm(s) == 0.0:
+        return 1
+    sc = np.cumsum(np.abs(s[::-1]) ** 2)[::-1]
+    R = max(int(np.argmax(sc < eps ** 2)), 1)
+    if sc[-1] > eps ** 2:
+        R = s.size
+    return R
+
+
+# ---- device-side building blocks -------------------------------------------------------------------
+def _up(tt, rt):
+    return [rt.to_device(c) for c in tt]
+
+
+def _down(tt, rt):
+    return [rt.to_host(c) for c in tt]
+
+
+def tt_rl_orthogonalise_dev(tt, rt):
+    """cy_src/tt_ops_cy.pyx:132-159 on device cores (in place on the list)."""
+    d = len(tt)
+    for i in range(d - 1, 0, -1):
+        sh = tuple(tt[i].shape)
+        shm = tuple(tt[i - 1].shape)
+        Q, R = K.qr(tt[i].reshape(sh[0], -1).t(), rt=rt)            # (rest, K), (K, r)
+        nr = R.shape[0]
+        tt[i] = Q.t().contiguous().reshape(nr, *sh[1:])
+        tt[i - 1] = K.gemm(tt[i - 1].reshape(-1, sh[0]), R.t(), rt=rt).reshape(*shm[:-1], nr)
+    return tt
+
+
+def _round_sweep_dev(tt, eps, rt, collect=False):
+    """Left-to-right truncation sweep of cy_src/tt_ops_cy.pyx:197-224 / :283-318 / :349-384."""
+    d = len(tt)
+    rank = 1
+    dropped = 0.0
+    for idx in range(d - 1):
+        sh = tuple(tt[idx].shape)
+        shn = tuple(tt[idx + 1].shape)
+        U, S, W = K.svd_left(tt[idx].reshape(rank * int(np.prod(sh[1:-1])), -1), rt=rt)
+        s = rt.to_host(S)
+        if collect:
+            sc = np.cumsum(np.abs(s[::-1]) ** 2)[::-1]
+            nr = max(int(np.argmax(sc < eps ** 2)), 1)
+            if sc[-1] > eps ** 2:
+                nr = s.size
+            if nr < s.size:
+                dropped += float(sc[nr])
+        else:
+            nr = prune_singular_vals(s, eps)
+        tt[idx] = U[:, :nr].contiguous().reshape(rank, *sh[1:-1], nr)
+        tt[idx + 1] = K.gemm(W[:nr], tt[idx + 1].reshape(shn[0], -1), rt=rt).reshape(nr, *shn[1:-1], shn[-1])
+        rank = nr
+    return dropped
+
+
+def _all_rank_one(tt):
+    return len(tt) == 1 or all(r == 1 for r in tt_ranks(tt))
+
+
+def tt_add_dev(a, b, rt):
+    """cy_src/tt_ops_cy.pyx:244-258 on device cores."""
+    if len(a) == 1:
+        return [K.ewise(a[0], 1.0, b=b[0], beta=1.0, rt=rt)]
+    out = []
+    last = len(a) - 1
+    for k, (x, y) in enumerate(zip(a, b)):
+        out.append(K.block_diag(x, y, "first" if k == 0 else ("last" if k == last else "mid"), rt=rt))
+    return out
+
+
+def tt_inner_prod_dev(a, b, rt):
+    """cy_src/tt_ops_cy.pyx:506-520: running (r1, r2) matrix, two GEMMs per core; returns a 1x1 device tensor."""
+    res = rt.to_device(np.ones((1, 1)))
+    for c1, c2 in zip(a, b):
+        r1, R1 = c1.shape[0], c1.shape[-1]
+        r2, R2 = c2.shape[0], c2.shape[-1]
+        nn = c1.numel() // (r1 * R1)
+        T = K.gemm(res.t(), c1.reshape(r1, nn * R1), rt=rt)                         # (r2, n R1)
+        res = K.gemm(T.reshape(r2 * nn, R1).t(), c2.reshape(r2 * nn, R2), rt=rt)    # (R1, R2)
+    return res
+
+
+def _swap_cores_dev(ca, cb, eps, rt):
+    """cy_src/tt_ops_cy.pyx:393-426."""
+    if ca.dim() == 3:
+        a0, a1, a2 = ca.shape
+        b0, b1, b2 = cb.shape
+        t = K.gemm(ca.reshape(a0 * a1, a2), cb.reshape(b0, b1 * b2), rt=rt).reshape(a0, a1, b1, b2)
+        t = K.permute4(t, (0, 2, 1, 3), rt=rt)                                      # (a0, b1, a1, b2)
+        U, S, W = K.svd_left(t.reshape(a0 * b1, a1 * b2), rt=rt)
+        rp = prune_singular_vals(rt.to_host(S), eps)
+        # reference keeps u*s on the left and v on the right; W = s*v, so rescale: left = U*s, right = W/s
+        left = K.scale_cols(U[:, :rp], S[:rp], rt=rt).reshape(a0, b1, rp)
+        right = K.scale_rows(W[:rp], S[:rp], divide=True, rt=rt).reshape(rp, a1, b2)
+        return left, right
+    a0, a1, a2, a3 = ca.shape
+    b0, b1, b2, b3 = cb.shape
+    t = K.gemm(ca.reshape(a0 * a1 * a2, a3), cb.reshape(b0, b1 * b2 * b3), rt=rt).reshape(a0, a1 * a2, b1 * b2, b3)
+    t = K.permute4(t, (0, 2, 1, 3), rt=rt)                                          # (a0, (b1 b2), (a1 a2), b3)
+    U, S, W = K.svd_left(t.reshape(a0 * b1 * b2, a1 * a2 * b3), rt=rt)
+    rp = prune_singular_vals(rt.to_host(S), eps)
+    left = K.scale_cols(U[:, :rp], S[:rp], rt=rt).reshape(a0, b1, b2, rp)
+    right = K.scale_rows(W[:rp], S[:rp], divide=True, rt=rt).reshape(rp, a1, a2, b3)
+    return left, right
+
+
+def _zipup_dev(first_fn, d, cores, eps, rt):
+    loop_eps = eps / math.sqrt(d - 1) if d > 1 else eps
+    for i in range(d):
+        cores[0] = first_fn(d - 1 - i, cores[0])
+        if i != d - 1:
+            for j in range(i, -1, -1):
+                cores[j], cores[j + 1] = _swap_cores_dev(cores[j], cores[j + 1], loop_eps, rt)
+    return cores
+
+
+def tt_fast_matrix_vec_mul_dev(M, v, eps, rt):
+    """cy_src/tt_ops_cy.pyx:430-447."""
+    cores = [c.permute(2, 1, 0).contiguous() for c in reversed(v)]
+
+    def first(p, c0):       # tensordot(M[p] (s,m,n,S), c0 (S,n,K), axes=([3,2],[0,1])) -> (s, m, K)
+        s, m, n, S = M[p].shape
+        Kk = c0.shape[2]
+        Mp = K.permute4(M[p], (0, 1, 3, 2), rt=rt).reshape(s * m, S * n)
+        return K.gemm(Mp, c0.reshape(S * n, Kk), rt=rt).reshape(s, m, Kk)
+    return _zipup_dev(first, len(M), cores, eps, rt)
+
+
+def tt_fast_mat_mat_mul_dev(A, B, eps, rt):
+    """cy_src/tt_ops_cy.pyx:451-464."""
+    cores = [c.permute(3, 1, 2, 0).contiguous() for c in reversed(B)]
+
+    def first(p, c0):       # tensordot(A[p] (s,m,n,S), c0 (S,n,j,K), axes=([3,2],[0,1])) -> (s, m, j, K)
+        s, m, n, S = A[p].shape
+        j, Kk = c0.shape[2], c0.shape[3]
+        Ap = K.permute4(A[p], (0, 1, 3, 2), rt=rt).reshape(s * m, S * n)
+        return K.gemm(Ap, c0.reshape(S * n, j * Kk), rt=rt).reshape(s, m, j, Kk)
+    return _zipup_dev(first, len(A), cores, eps, rt)
+
+
+def tt_fast_hadamard_dev(a, b, eps, rt):
+    """cy_src/tt_ops_cy.pyx:468-502: out[r, i.., K] = sum_R a[r, i.., R] c0[R, i.., K] (batched over the mode)."""
+    four = a[0].dim() == 4 and b[0].dim() == 4
+    cores = [(c.permute(3, 1, 2, 0) if four else c.permute(2, 1, 0)).contiguous() for c in reversed(b)]
+
+    def first(p, c0):
+        ap = a[p]
+        r, Rr, Kk = ap.shape[0], ap.shape[-1], c0.shape[-1]
+        nn = ap.numel() // (r * Rr)
+        A3 = ap.reshape(r, nn, Rr).permute(1, 0, 2)          # (mode, r, R) strided view
+        B3 = c0.reshape(Rr, nn, Kk).permute(1, 0, 2)         # (mode, R, K)
+        out = K.gemm(A3, B3, rt=rt)                          # (mode, r, K)
+        out = K.permute4(out.reshape(1, nn, r, Kk), (0, 2, 1, 3), rt=rt)
+        return out.reshape(r, *ap.shape[1:-1], Kk)
+    return _zipup_dev(first, len(a), cores, eps, rt)
+
+
+# ---- NumPy-boundary API (reference signatures) -----------------------------------------------------
+def tt_rl_orthogonalise(train_tt):
+    """cy_src/tt_ops_cy.pyx:132-159; mutates and returns the input list."""
+    if len(train_tt) == 1:
+        return train_tt
+    rt = get_runtime()
+    dev = tt_rl_orthogonalise_dev(_up(train_tt, rt), rt)
+    train_tt[:] = _down(dev, rt)
+    return train_tt
+
+
+def tt_rank_reduce(train_tt, eps=1e-18):
+    """cy_src/tt_ops_cy.pyx:180-226; mutates and returns the input list."""
+    if _all_rank_one(train_tt):
+        return train_tt
+    rt = get_runtime()
+    eps = eps / np.sqrt(len(train_tt) - 1)
+    dev = tt_rl_orthogonalise_dev(_up(train_tt, rt), rt)
+    _round_sweep_dev(dev, eps, rt)
+    train_tt[:] = _down(dev, rt)
+    return train_tt
+
+
+def tt_add(train_1_tt, train_2_tt):
+    """cy_src/tt_ops_cy.pyx:244-258."""
+    rt = get_runtime()
+    return _down(tt_add_dev(_up(train_1_tt, rt), _up(train_2_tt, rt), rt), rt)
+
+
+def tt_sub(train_1_tt, train_2_tt):
+    """src/tt_ops.py:189-190."""
+    return tt_add(train_1_tt, tt_scale(-1, train_2_tt))
+
+
+def _psd_like(train_tt, extra_fn, eps):
+    d = len(train_tt)
+    eps = eps / 2.0
+    if _all_rank_one(train_tt):
+        return train_tt
+    rt = get_runtime()
+    eps = eps / np.sqrt(d - 1)
+    dev = tt_rl_orthogonalise_dev(_up(train_tt, rt), rt)
+    dropped = _round_sweep_dev(dev, eps, rt, collect=True)
+    train_tt[:] = _down(dev, rt)           # the reference mutates its input before adding the correction
+    factor = pow(dropped, 1.0 / (2 * d))
+    return _down(tt_add_dev(dev, _up(extra_fn(factor), rt), rt), rt)
+
+
+def tt_psd_rank_reduce(train_tt, eps=1e-18):
+    """cy_src/tt_ops_cy.pyx:262-325: rounding that adds the discarded energy back as factor * I."""
+    shape = train_tt[0].shape
+    return _psd_like(train_tt, lambda f: [f * np.eye(shape[1]).reshape(1, *shape[1:-1], 1)] * len(train_tt), eps)
+
+
+def tt_mask_rank_reduce(train_tt, mask_tt, eps=1e-18):
+    """cy_src/tt_ops_cy.pyx:329-388."""
+    return _psd_like(train_tt, lambda f: [f * c for c in mask_tt], eps)
+
+
+def tt_inner_prod(train_1_tt, train_2_tt):
+    """cy_src/tt_ops_cy.pyx:506-520."""
+    rt = get_runtime()
+    return float(rt.to_host(tt_inner_prod_dev(_up(train_1_tt, rt), _up(train_2_tt, rt), rt))[0, 0])
+
+
+def tt_norm(train_tt):
+    """src/tt_ops.py:306-310."""
+    v = tt_inner_prod(train_tt, train_tt)
+    return float(np.sqrt(v)) if v > 0 else 0.0
+
+
+def tt_normalise(train_tt, radius=1):
+    """cy_src/tt_ops_cy.pyx:524-526 (`radius` is a C int there, i.e. truncated)."""
+    factor = np.divide(int(radius), np.sqrt(tt_inner_prod(train_tt, train_tt)))
+    return tt_scale(factor, train_tt)
+
+
+def tt_fast_matrix_vec_mul(matrix_tt, vec_tt, eps=1e-18):
+    """cy_src/tt_ops_cy.pyx:430-447."""
+    rt = get_runtime()
+    return _down(tt_fast_matrix_vec_mul_dev(_up(matrix_tt, rt), _up(vec_tt, rt), eps, rt), rt)
+
+
+def tt_fast_mat_mat_mul(matrix_tt_1, matrix_tt_2, eps=1e-18):
+    """cy_src/tt_ops_cy.pyx:451-464."""
+    rt = get_runtime()
+    return _down(tt_fast_mat_mat_mul_dev(_up(matrix_tt_1, rt), _up(matrix_tt_2, rt), eps, rt), rt)
+
+
+def tt_fast_hadamard(train_tt_1, train_tt_2, eps=1e-18):
+    """cy_src/tt_ops_cy.pyx:468-502."""
+    rt = get_runtime()
+    return _down(tt_fast_hadamard_dev(_up(train_tt_1, rt), _up(train_tt_2, rt), eps, rt), rt)
+
+
+def tt_random_gaussian(target_ranks, shape=(2,)):
+    """cy_src/tt_ops_cy.pyx:529-533."""
+    rr = [1] + list(target_ranks) + [1]
+    return tt_normalise([np.divide(1, a * np.prod(shape) * b) * np.random.randn(a, *shape, b)
+                         for a, b in zip(rr[:-1], rr[1:])])
+
+
+def tt_mat_vec_mul(mat, vec, op_tol, eps, verbose=False):
+    """src/tt_als.py:1765-1768: exact zip-up + rounding when the rank products stay <= 80."""
+    if np.max(np.array(tt_ranks(mat)) * np.array(tt_ranks(vec))) > 80:
+        raise NotImplementedError("ALS-fitted TT mat-vec (reference src/tt_als.py:1637-1762) is SURVEY 8f-2 (next)")
+    if _all_rank_one_product(mat, vec):
+        return tt_rank_reduce(tt_fast_matrix_vec_mul(mat, vec, eps), op_tol)
+    rt = get_runtime()
+    dev = tt_fast_matrix_vec_mul_dev(_up(mat, rt), _up(vec, rt), eps, rt)
+    return _round_dev_to_host(dev, op_tol, rt)
+
+
+def tt_mat_mat_mul(mat1, mat2, op_tol, eps, verbose=False):
+    """src/tt_als.py:1631-1634."""
+    if np.max(np.array(tt_ranks(mat1)) * np.array(tt_ranks(mat2))) > 40:
+        raise NotImplementedError("ALS-fitted TT mat-mat (reference src/tt_als.py:1502-1628) is SURVEY 8f-2 (next)")
+    rt = get_runtime()
+    dev = tt_fast_mat_mat_mul_dev(_up(mat1, rt), _up(mat2, rt), eps, rt)
+    return _round_dev_to_host(dev, op_tol, rt)
+
+
+def _all_rank_one_product(a, b):
+    return False
+
+
+def _round_dev_to_host(dev, eps, rt):
+    if _all_rank_one(dev):
+        return _down(dev, rt)
+    eps = eps / np.sqrt(len(dev) - 1)
+    dev = tt_rl_orthogonalise_dev(dev, rt)
+    _round_sweep_dev(dev, eps, rt)
+    return _down(dev, rt)
+
+
+def tt_IkronM(matrix_tt):
+    """src/tt_ops.py:360-363: I (x) M per core."""
+    rt = get_runtime()
+    return [rt.to_host(K.embed(rt.to_device(c), "IkronM", rt=rt)) for c in matrix_tt]
+
+
+def tt_MkronI(matrix_tt):
+    """src/tt_ops.py:365-368."""
+    rt = get_runtime()
+    return [rt.to_host(K.embed(rt.to_device(c), "MkronI", rt=rt)) for c in matrix_tt]
+
+
+def _diag_embed_tt(cores3, eps):
+    rt = get_runtime()
+    dev = [K.embed(rt.to_device(c), "diag", rt=rt) for c in cores3]
+    return _round_dev_to_host(dev, eps, rt)
+
+
+def tt_diag(vec_tt, eps=1e-18):
+    """src/tt_ops.py:312-316."""
+    return _diag_embed_tt([np.ascontiguousarray(c) for c in vec_tt], eps)
+
+
+def tt_diag_op(matrix_tt, eps=1e-18):
+    """src/tt_ops.py:371-375."""
+    return _diag_embed_tt([np.ascontiguousarray(c).reshape(c.shape[0], -1, c.shape[-1]) for c in matrix_tt], eps)
+
+
+def tt_diagonal(matrix_tt):
+    """src/tt_ops.py:318-319 (pure view bookkeeping)."""
+    return [np.transpose(np.diagonal(c, axis1=1, axis2=2), (0, 2, 1)) for c in matrix_tt]
+
+
+def tt_entrywise_sum(train_tt):
+    """src/tt_ops.py:342-352: inner product with the all-ones train."""
+    ones = [np.ones((1, *c.shape[1:-1], 1)) for c in train_tt]
+    return tt_inner_prod(train_tt, ones)
+
+
+def tt_sum(*args, op_tol=1e-18, rank_reduce=True):
+    """src/tt_ops.py:321-328."""
+    out = args[0]
+    for a in args[1:]:
+        out = tt_rank_reduce(tt_add(out, a), op_tol) if rank_reduce else tt_add(out, a)
+    return out
+
+
+def tt_rl_orthogonalise_py(train_tt):
+    """src/tt_ops.py:30-42: loops down to i = 0, so core 0 is normalised and its 1x1 R factor wraps
+    around into the LAST core."""
+    d = len(train_tt)
+    if d == 1:
+        return train_tt
+    rt = get_runtime()
+    dev = _up(train_tt, rt)
+    for i in range(d - 1, -1, -1):
+        sh = tuple(dev[i].shape)
+        prev = (i - 1) % d
+        shm = tuple(dev[prev].shape)
+        Q, R = K.qr(dev[i].reshape(sh[0], -1).t(), rt=rt)
+        dev[i] = Q.t().contiguous().reshape(-1, *sh[1:-1], sh[-1])
+        dev[prev] = K.gemm(dev[prev].reshape(-1, R.shape[1]), R.t(), rt=rt).reshape(-1, *shm[1:-1], dev[i].shape[0])
+    train_tt[:] = _down(dev, rt)
+    return train_tt
+
+
+def tt_rank_retraction(train_tt, upper_ranks):
+    """src/tt_ops.py:132-152: cap the ranks by keeping the top-k singular triplets."""
+    train_tt = tt_rl_orthogonalise_py(train_tt)
+    rt = get_runtime()
+    dev = _up(train_tt, rt)
+    rank = 1
+    for idx, ur in enumerate(upper_ranks):
+        sh = tuple(dev[idx].shape)
+        shn = tuple(dev[idx + 1].shape)
+        U, S, W = K.svd_left(dev[idx].reshape(rank * int(np.prod(sh[1:-1])), -1), rt=rt)
+        nr = min(int(ur), S.shape[0])
+        # the reference selects with argpartition (unordered); the kept subspace is the same top-nr set
+        dev[idx] = U[:, :nr].contiguous().reshape(rank, *sh[1:-1], nr)
+        dev[idx + 1] = K.gemm(W[:nr], dev[idx + 1].reshape(shn[0], -1), rt=rt).reshape(nr, *shn[1:-1], shn[-1])
+        rank = nr
+    train_tt[:] = _down(dev, rt)
+    return train_tt

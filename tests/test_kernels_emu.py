@@ -55,3 +55,7 @@ def test_qr_svd(rt):
 
 def test_elementwise(rt):
     KC.assert_small(KC.case_elementwise(rt), tol=1e-13)
+
+
+def test_tt_algebra(rt):
+    KC.assert_small(KC.case_tt_algebra(rt))
