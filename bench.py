@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the TT-IPM Newton-system hot path (block AMEn KKT solve) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload maxcut_10] [--impl reference]
+
+One "step" = one pass of the hot path over the workload: every KKT system traced from the reference
+IPM run of the named config (tests/golden/amen_<config>_*.npz: operator blocks, right-hand sides,
+warm starts, RNG state) is solved with the device-resident block AMEn sweep.  The metric is
+BASELINE.json's "TT-IPM solve time (s)" restricted to the path: seconds per Newton-system solve.
+
+  value     : device-resident time (operator cores, rhs and warm start already in HBM), CUDA events
+  e2e       : the same solves through the host-facing entry (NumPy cores in, NumPy cores out):
+              H2D of every core and D2H of the solution inside the timed region
+  roofline  : dominant kernel = the persistent LGMRES kernel (fp64 DMMA contractions), algorithmic
+              flops / CUDA-event time of its launches, against cuBLAS DGEMM measured in this run
+  cpu_baseline / --impl reference : the oracle (NumPy port of the reference path; the reference itself
+              and PETSc are not on the GPU box) on the host cores, same systems
+Multi-GPU: the sweep is sequential, so ranks are independent replicas (one problem instance per GPU,
+no data-path collective): scaling = "weak", time = max over ranks.
+"""
+import argparse
+import glob
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "tensor-train-interior-point-method_b200"), os.path.join(ROOT, "tests"),
+          os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    "maxcut_10": ("amen_maxcut_10_r1_s41_*.npz", "MaxCut dim 10 rank 1 seed 41 (configs/maxcut_10.yaml)"),
+    "maxcut_13": ("amen_maxcut_13_r2_s83_*.npz", "MaxCut dim 13 rank 2 seed 83 (configs/maxcut_13.yaml), IPM iteration 1"),
+    "corr_clust_8": ("amen_corr_clust_8_r1_s208_*.npz", "Correlation clustering dim 8 rank 1 seed 208"),
+    "max_stable_set_9": ("amen_max_stable_set_9_r1_s876_*.npz", "Max stable set dim 9 rank 1 seed 876"),
+    "graphm_3": ("amen_graphm_3_r2_s256_*.npz", "Graph matching dim 3 rank 2 seed 256, IPM iteration 0"),
+}
+
+
+def load_systems(workload):
+    import golden_io as G
+    pat, _ = WORKLOADS[workload]
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", pat)))
+    if not files:
+        raise SystemExit(f"no fixtures for workload {workload}")
+    return [G.load_amen(f) for f in files]
+
+
+def term_flops(r, R, s, S, n=4):
+    """SURVEY 8d, the reference's 3-GEMM order: 2 r n R R S + 2 r R s n n S + 2 r n R r s."""
+    return 2.0 * r * n * R * R * S + 2.0 * r * R * s * n * n * S + 2.0 * r * n * R * r * s
+
+
+class Clocks(threading.Thread):
+    """nvidia-smi sampler for the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                parts = [x.strip() for x in out.split(",")]
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for nm, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def oracle_solve(g):
+    import tt_oracle as O
+    bm = O.BlockMatrix(g["A"], g["aliases"], g["transposes"])
+    bv = O.BlockVector(g["b"])
+    ls = O.local_solver_ineq if g["ineq"] else O.local_solver_eq
+    np.random.set_state(g["rng_state"])
+    x0 = [c.copy() for c in g["x0"]] if g["x0"] is not None else None
+    if x0 is not None:
+        x0 = O.tt_rank_retraction(x0, [len(x0)] * (len(x0) - 1))
+    stats = []
+
+    def solver(*a, **k):
+        return ls(*a, stats=stats, **k)
+    x, res, st = O.tt_block_amen(bm, bv, g["termination_tol"], r_max=g["rank_restriction"], eps=g["eps"],
+                                 nswp=g["inner_m"], x0=x0, local_solver=solver, kick_rank=2, amen=True)
+    return x, res, stats
+
+
+def host_threads():
+    try:
+        import threadpoolctl
+        info = threadpoolctl.threadpool_info()
+        return max([i.get("num_threads", 1) for i in info] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    systems = load_systems(args.workload)
+    budget = 150.0
+    t_start = time.perf_counter()
+    done = 0
+    for _ in range(args.warmup):
+        if time.perf_counter() - t_start > budget * 0.3:
+            break
+        oracle_solve(systems[0])
+    times = []
+    for step in range(args.steps):
+        t0 = time.perf_counter()
+        for g in systems:
+            oracle_solve(g)
+        times.append(time.perf_counter() - t0)
+        done += 1
+        if time.perf_counter() - t_start > budget:
+            break
+    per_solve = float(np.mean(times)) / len(systems)
+    cores = host_threads()
+    line = {"impl": "reference", "metric": "tt_ipm_newton_system_solve_time", "value": per_solve, "unit": "s",
+            "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][1]}; {len(systems)} traced KKT systems",
+                       "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": per_solve, "unit": "s", "cores": cores, "kind": "port",
+                             "sample": f"{done} passes over the {len(systems)} systems"},
+            "e2e": {"value": per_solve, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def measure_dgemm_peak(torch, dev):
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        a @ b
+    torch.cuda.synchronize(dev)
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    return 2.0 * n ** 3 / best / 1e12
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="maxcut_10", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from ttipm_b200 import get_runtime, kernels as K
+    from ttipm_b200.amen import DeviceBlockAmen
+    import tt_oracle as O
+    rt = get_runtime()
+    systems = load_systems(args.workload)
+
+    # ---- problem set-up (not timed): upload operator blocks / rhs, retract warm starts like the reference ----
+    def make(g):
+        solver = DeviceBlockAmen(g["A"], g["aliases"], g["transposes"], g["b"], g["ineq"], rt=rt)
+        return solver
+
+    def host_x0(g):
+        np.random.set_state(g["rng_state"])
+        x0 = [c.copy() for c in g["x0"]] if g["x0"] is not None else None
+        if x0 is not None:
+            x0 = O.tt_rank_retraction(x0, [len(x0)] * (len(x0) - 1))   # host set-up of the bench input only
+        return x0
+
+    x0s = [host_x0(g) for g in systems]
+    rng_after = []
+    for g in systems:
+        rng_after.append(g["rng_state"])
+
+    def device_pass(profile=None):
+        """value leg: everything resident, only the sweeps are timed."""
+        states = []
+        solvers = []
+        for g, x0 in zip(systems, x0s):
+            np.random.set_state(g["rng_state"])
+            s = make(g)
+            st = s.prepare([c.copy() for c in x0] if x0 is not None else None, 2, True)
+            solvers.append(s)
+            states.append(st)
+        rt.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = rt.launches
+        e0.record()
+        outs = []
+        for g, s, st in zip(systems, solvers, states):
+            if profile is not None:
+                s.stats["profile"] = profile
+            outs.append(s.run(st, g["termination_tol"], g["rank_restriction"], g["eps"], g["inner_m"]))
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) * 1e-3, rt.launches - l0, solvers, outs
+
+    def e2e_pass():
+        """e2e leg: NumPy cores in, NumPy cores out, H2D/D2H inside the timed region."""
+        h2d = d2h = 0
+        rt.sync()
+        t0 = time.perf_counter()
+        for g, x0 in zip(systems, x0s):
+            np.random.set_state(g["rng_state"])
+            s = make(g)
+            h2d += sum(c.nbytes for cores in g["A"].values() for c in cores)
+            h2d += sum(c.nbytes for cores in g["b"].values() for c in cores)
+            x, res = s.solve(g["termination_tol"], r_max=g["rank_restriction"], eps=g["eps"], nswp=g["inner_m"],
+                             x0=[c.copy() for c in x0] if x0 is not None else None, kick_rank=2, amen=True)
+            h2d += sum(c.nbytes for c in x0) if x0 is not None else 0
+            d2h += sum(c.nbytes for c in x)
+        rt.sync()
+        return time.perf_counter() - t0, h2d, d2h
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        device_pass()
+    clocks = Clocks(local_rank)
+    clocks.start()
+    barrier()
+    times, launches = [], 0
+    for _ in range(args.steps):
+        t, nl, solvers, outs = device_pass()
+        times.append(t)
+        launches += nl
+    barrier()
+    total = float(np.sum(times))
+    e2e_times = []
+    for _ in range(max(2, min(args.steps, 5))):
+        t, h2d, d2h = e2e_pass()
+        e2e_times.append(t)
+    clocks.stop_flag = True
+    clocks.join(timeout=2)
+    if world > 1:
+        tt_ = torch.tensor([total, float(np.mean(e2e_times))], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+        total, e2e_mean = float(tt_[0]), float(tt_[1])
+    else:
+        e2e_mean = float(np.mean(e2e_times))
+
+    # ---- roofline of the dominant kernel (persistent LGMRES): one instrumented pass ---------------------
+    prof = []
+    t_prof, _, solvers, outs = device_pass(profile=prof)
+    lg_time = lg_flops = 0.0
+    lg_calls = lg_its = 0
+    for ev0, ev1, info, shape in prof:
+        ms = ev0.elapsed_time(ev1)
+        inf = rt.to_host(info)
+        its, mv = float(inf[0]), float(inf[1])
+        nv = shape["nv"]
+        fl = mv * shape["mv_flops"] + 4.0 * nv * (its * (its + 1) / 2.0 if its <= shape["restart"] else
+                                                  its * (shape["restart"] + 1) / 2.0)
+        lg_time += ms * 1e-3
+        lg_flops += fl
+        lg_calls += 1
+        lg_its += int(its)
+    res_check = [float(o[1]) for o in outs]
+
+    if rank == 0:
+        nsys = len(systems)
+        per_solve = total / args.steps / nsys
+        peak = measure_dgemm_peak(torch, dev)
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm = json.load(open(peaks_file))["hbm_gbs"] if os.path.exists(peaks_file) else 6650.0
+        achieved = lg_flops / lg_time / 1e12 if lg_time > 0 else 0.0
+        line = {
+            "metric": "tt_ipm_newton_system_solve_time", "value": per_solve, "unit": "s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][1]}; {nsys} KKT systems traced from the "
+                                   "reference IPM run (block AMEn solve of each = 1 step)",
+                       "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "l2": "working set << L2 by construction of the problem (TT cores of KBs); every step re-uploads "
+                             "nothing and re-runs all kernels, no result is cached between steps"},
+            "e2e": {"value": e2e_mean / nsys, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "tensor", "kernel": "k_lgmres (persistent LGMRES, fp64 DMMA local matvec + CGS)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         "traffic": None, "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has "
+                                                         "no fp64 figure)", "launches": lg_calls, "inner_iterations": lg_its,
+                         "kernel_share_of_step": lg_time / t_prof if t_prof > 0 else None, "hbm_gbs_measured": hbm},
+            "final_local_residuals": res_check,
+        }
+        if not args.no_cpu_baseline:
+            t0 = time.perf_counter()
+            for g in systems:
+                oracle_solve(g)
+            cpu = (time.perf_counter() - t0) / nsys
+            line["cpu_baseline"] = {"value": cpu, "unit": "s", "cores": host_threads(), "kind": "port",
+                                    "sample": f"one pass over the same {nsys} systems with the NumPy/SciPy oracle"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -194,7 +194,7 @@ class _Budget(BaseException):
     pass
 
 
-def amen(problem, dim, rank, seed, which, budget_s, local=False):
+def amen(problem, dim, rank, seed, which, budget_s, local=False, inputs_only=False):
     """Trace calls of tt_restarted_block_amen made by the reference IPM."""
     ref = ref_env.load()
     ipm, ALS = ref.tt_ipm, ref.tt_als
@@ -265,6 +265,15 @@ def amen(problem, dim, rank, seed, which, budget_s, local=False):
             t0 = time.time()
         if time.time() - t_start > budget_s and not rec:
             raise _Budget()
+        if rec and inputs_only:
+            out["wall_s"] = np.array(np.nan)
+            out["raised"] = np.array(0)
+            out["trace"] = np.zeros((0, 5))
+            path = os.path.join(GOLD, f"amen_{tag}_{idx}.npz")
+            np.savez_compressed(path, **out)
+            print(f"wrote {path} (inputs only, {os.path.getsize(path) / 1e3:.0f} kB)", flush=True)
+            if idx >= max(which):
+                raise _Budget()
         err = None
         try:
             x, res = orig(block_A, block_b, rank_restriction, op_tol, termination_tol=termination_tol, eps=eps,
@@ -326,6 +335,7 @@ if __name__ == "__main__":
         if "--budget" in sys.argv:
             budget = float(sys.argv[sys.argv.index("--budget") + 1])
         amen(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]),
-             set(int(v) for v in sys.argv[6].split(",")), budget, local="--local" in sys.argv)
+             set(int(v) for v in sys.argv[6].split(",")), budget, local="--local" in sys.argv,
+             inputs_only="--inputs-only" in sys.argv)
     elif cmd == "e2e":
         e2e(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))

@@ -4,9 +4,9 @@
 // CPU-only test tier can execute the real kernel sources on tiny shapes before
 // GPU time is spent; the product library (libttipm_b200.so) never includes it.
 #pragma once
-#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <ucontext.h>
 #include <atomic>
 #include <functional>
 #include <thread>
@@ -22,74 +22,109 @@
 typedef void* tt_stream_t;
 typedef int cudaError_t;
 
+// Each CUDA thread is a user-level fiber (ucontext); one OS thread runs all fibers of a CTA round-robin.
+// Barriers are counters that waiting fibers poll between yields, so any mix of block- and warp-level
+// rendezvous works.  CTAs of a cooperative launch run on separate OS threads.
 namespace emu {
 struct Dim3 {
     unsigned x = 1, y = 1, z = 1;
     Dim3() {}
     Dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
+struct Barrier {
+    unsigned n = 0, count = 0, gen = 0;
+};
+struct Fiber {
+    ucontext_t ctx;
+    char* stack = nullptr;
+    bool done = false;
+};
 struct Cta {
-    pthread_barrier_t bar;
-    std::vector<pthread_barrier_t> wbar;
+    Barrier bar;
+    std::vector<Barrier> wbar;
     std::vector<double> xa, xb;   // per-warp exchange buffers (32 doubles each)
     unsigned char* smem = nullptr;
+    std::vector<Fiber> fibers;
+    ucontext_t sched;
+    int current = 0;
+    Dim3 grid, block, bidx;
+    const std::function<void()>* body = nullptr;
 };
 extern thread_local Dim3 threadIdx_, blockIdx_, blockDim_, gridDim_;
 extern thread_local Cta* cta;
 
-inline void run_cta(Dim3 grid, Dim3 block, size_t smem, Dim3 bidx, const std::function<void()>& body,
-                    std::vector<std::thread>& pool, std::vector<Cta*>& ctas) {
-    const unsigned nt = block.x, nw = (nt + 31) / 32;
-    Cta* c = new Cta();
-    pthread_barrier_init(&c->bar, nullptr, nt);
-    c->wbar.resize(nw);
-    for (unsigned w = 0; w < nw; ++w) {
-        unsigned cnt = (w + 1) * 32 <= nt ? 32 : nt - w * 32;
-        pthread_barrier_init(&c->wbar[w], nullptr, cnt);
+inline void yield_fiber() {
+    Cta* c = cta;
+    swapcontext(&c->fibers[c->current].ctx, &c->sched);
+}
+inline void barrier_wait(Barrier& b) {
+    const unsigned gen = b.gen;
+    if (++b.count == b.n) {
+        b.count = 0;
+        ++b.gen;
+        return;
     }
-    c->xa.assign(nw * 32, 0.0);
-    c->xb.assign(nw * 32, 0.0);
-    c->smem = (unsigned char*)aligned_alloc(64, ((smem + 63) / 64 + 1) * 64);
-    memset(c->smem, 0xCD, smem);   // poison: uninitialised shared memory reads show up
-    ctas.push_back(c);
-    for (unsigned t = 0; t < nt; ++t) {
-        pool.emplace_back([=, &body]() {
-            threadIdx_ = Dim3(t);
-            blockIdx_ = bidx;
-            blockDim_ = block;
-            gridDim_ = grid;
-            cta = c;
-            body();
-        });
-    }
+    while (b.gen == gen) yield_fiber();
+}
+inline void fiber_entry() {
+    Cta* c = cta;
+    (*c->body)();
+    c->fibers[c->current].done = true;
+    swapcontext(&c->fibers[c->current].ctx, &c->sched);
 }
 
-inline void free_ctas(std::vector<Cta*>& ctas) {
-    for (Cta* c : ctas) {
-        pthread_barrier_destroy(&c->bar);
-        for (auto& b : c->wbar) pthread_barrier_destroy(&b);
-        free(c->smem);
-        delete c;
+inline void run_cta(Dim3 grid, Dim3 block, size_t smem, Dim3 bidx, const std::function<void()>& body) {
+    const unsigned nt = block.x, nw = (nt + 31) / 32;
+    const size_t stack_bytes = 256 * 1024;
+    Cta c;
+    c.bar.n = nt;
+    c.wbar.resize(nw);
+    for (unsigned w = 0; w < nw; ++w) c.wbar[w].n = (w + 1) * 32 <= nt ? 32 : nt - w * 32;
+    c.xa.assign(nw * 32, 0.0);
+    c.xb.assign(nw * 32, 0.0);
+    c.smem = (unsigned char*)aligned_alloc(64, ((smem + 63) / 64 + 1) * 64);
+    memset(c.smem, 0xCD, smem);   // poison: uninitialised shared memory reads show up
+    c.grid = grid; c.block = block; c.bidx = bidx; c.body = &body;
+    c.fibers.resize(nt);
+    cta = &c;
+    blockIdx_ = bidx; blockDim_ = block; gridDim_ = grid;
+    for (unsigned t = 0; t < nt; ++t) {
+        Fiber& f = c.fibers[t];
+        f.stack = (char*)malloc(stack_bytes);
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = stack_bytes;
+        f.ctx.uc_link = &c.sched;
+        makecontext(&f.ctx, (void (*)())fiber_entry, 0);
     }
-    ctas.clear();
+    unsigned alive = nt;
+    while (alive) {
+        for (unsigned t = 0; t < nt; ++t) {
+            Fiber& f = c.fibers[t];
+            if (f.done) continue;
+            c.current = (int)t;
+            threadIdx_ = Dim3(t);
+            swapcontext(&c.sched, &f.ctx);
+            if (f.done) --alive;
+        }
+    }
+    for (auto& f : c.fibers) free(f.stack);
+    free(c.smem);
+    cta = nullptr;
 }
 
 // concurrent = all CTAs alive at once (needed by kernels that use grid_sync)
 inline void launch(Dim3 grid, Dim3 block, size_t smem, bool concurrent, const std::function<void()>& body) {
     std::vector<std::thread> pool;
-    std::vector<Cta*> ctas;
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
-                run_cta(grid, block, smem, Dim3(bx, by, bz), body, pool, ctas);
-                if (!concurrent) {
-                    for (auto& th : pool) th.join();
-                    pool.clear();
-                    free_ctas(ctas);
-                }
+                if (concurrent && grid.x * grid.y * grid.z > 1)
+                    pool.emplace_back([=, &body]() { run_cta(grid, block, smem, Dim3(bx, by, bz), body); });
+                else
+                    run_cta(grid, block, smem, Dim3(bx, by, bz), body);
             }
     for (auto& th : pool) th.join();
-    free_ctas(ctas);
 }
 }  // namespace emu
 typedef ::emu::Dim3 dim3;
@@ -99,8 +134,8 @@ typedef ::emu::Dim3 dim3;
 #define blockDim (::emu::blockDim_)
 #define gridDim (::emu::gridDim_)
 
-static inline void __syncthreads() { pthread_barrier_wait(&::emu::cta->bar); }
-static inline void __syncwarp() { pthread_barrier_wait(&::emu::cta->wbar[threadIdx.x >> 5]); }
+static inline void __syncthreads() { ::emu::barrier_wait(::emu::cta->bar); }
+static inline void __syncwarp() { ::emu::barrier_wait(::emu::cta->wbar[::emu::cta->current >> 5]); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) {
     return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
@@ -137,7 +172,6 @@ static inline void dmma884(double a, double b, double& c0, double& c1) {
 }
 static inline unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v = __atomic_load_n(p, __ATOMIC_ACQUIRE);
-    if (v == 0xFFFFFFFFu) std::this_thread::yield();
     std::this_thread::yield();
     return v;
 }

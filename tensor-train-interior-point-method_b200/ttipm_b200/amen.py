@@ -128,7 +128,7 @@ class DeviceBlockAmen:
                 prev = x[k]
                 sys_ = self._local_system(st, k)
                 sol, r_old, r_new, rhs, norm_rhs, st.direct_solve_failure = solve_local(
-                    sys_, prev, 3 * d, not st.direct_solve_failure, self.ineq, stats=self.stats["lgmres"])
+                    sys_, prev, 3 * d, not st.direct_solve_failure, self.ineq, stats=self.stats)
                 self.stats["local_solves"] += 1
                 self.trace.append((swp, k, r_old, r_new, prev.shape[0] * prev.shape[3]))
                 local_res = max(local_res, r_old)
@@ -270,9 +270,9 @@ class DeviceBlockAmen:
         return local_res, local_dx
 
     # ------------------------------------------------------------------------------------------
-    def solve(self, term_tol, r_max=100, eps=1e-12, nswp=22, x0=None, kick_rank=2, amen=True):
-        """tt_block_amen (reference src/tt_als.py:525-670); x0: list of numpy cores or None.
-        Returns (x_cores as numpy list, final local residual)."""
+    def prepare(self, x0=None, kick_rank=2, amen=True):
+        """Host part of tt_block_amen's set-up (reference src/tt_als.py:527-585): validate the warm start,
+        draw the random residual train in the reference's RNG order and upload everything once."""
         rt = self.rt
         bs = self.block_size
         model = next(iter(self.b.values()))
@@ -280,7 +280,9 @@ class DeviceBlockAmen:
 
         def fresh():
             from . import tt as T
-            cores = T.tt_normalise([np.random.randn(1, *x_shape, 1) for _ in model[:-1]])
+            from .runtime import use_runtime
+            with use_runtime(rt):
+                cores = T.tt_normalise([np.random.randn(1, *x_shape, 1) for _ in model[:-1]])
             return cores + [np.random.randn(1, bs, *x_shape, 1)]
 
         direction = 1
@@ -294,10 +296,12 @@ class DeviceBlockAmen:
             elif where[0] == 0:
                 direction = -1
         st = _State()
+        st.direction = direction
         st.N = [c.shape[-2] for c in xh]
         st.d = d = len(st.N)
         st.rx = np.array([1] + [c.shape[0] for c in xh[1:]] + [1])
         st.amen = amen
+        st.kick_rank = kick_rank
         one3 = lambda: rt.to_device(np.ones((1, 1, 1)))
         one2 = lambda: rt.to_device(np.ones((1, 1)))
         keys = list(self.A.keys())
@@ -305,7 +309,6 @@ class DeviceBlockAmen:
         st.XAX = [{key: one3() for key in keys}] + [dict() for _ in range(d - 1)] + [{key: one3() for key in keys}]
         st.Xb = [{i: one2() for i in rows}] + [dict() for _ in range(d - 1)] + [{i: one2() for i in rows}]
         st.ZAX = st.Zb = st.z = st.rz = None
-        zh = None
         if amen:
             tk = _tkeys(keys, self.transposes)
             st.ZAX = [{key: one3() for key in tk}] + [dict() for _ in range(d - 1)] + [{key: one3() for key in tk}]
@@ -318,9 +321,16 @@ class DeviceBlockAmen:
             st.rz = np.array([1] + [c.shape[0] for c in zh[1:]] + [1])
             st.z = [rt.to_device(c) for c in zh]
         st.x = [rt.to_device(c) for c in xh]
-        st.eps, st.r_max, st.kick_rank = eps, r_max, kick_rank
+        return st
+
+    def run(self, st, term_tol, r_max=100, eps=1e-12, nswp=22):
+        """The sweeps of tt_block_amen (reference src/tt_als.py:586-670) on a prepared, device-resident state.
+        Returns (device cores, final local residual)."""
+        d = st.d
+        st.eps, st.r_max = eps, r_max
         st.trunc_tol = term_tol / math.sqrt(d)
         st.direct_solve_failure = False
+        direction = st.direction
         last = False
         final_res = math.inf
         self.sweeps = 0
@@ -334,4 +344,11 @@ class DeviceBlockAmen:
                 final_res = local_res
             direction *= -1
         self.ranks = [int(v) for v in st.rx[1:-1]]
-        return [rt.to_host(c) for c in st.x], final_res
+        return st.x, final_res
+
+    def solve(self, term_tol, r_max=100, eps=1e-12, nswp=22, x0=None, kick_rank=2, amen=True):
+        """tt_block_amen (reference src/tt_als.py:525-670); x0: list of numpy cores or None.
+        Returns (x_cores as numpy list, final local residual)."""
+        st = self.prepare(x0, kick_rank, amen)
+        xd, final_res = self.run(st, term_tol, r_max, eps, nswp)
+        return [self.rt.to_host(c) for c in xd], final_res

@@ -197,9 +197,22 @@ def solve_local(sys_, prev, size_limit, dense_solve, ineq, rtol=1e-5, stats=None
             lrhs = diff
         restart = min(m, 100)
         aug = max(restart // 10, 3)
+        prof = stats.get("profile") if stats is not None else None
+        if prof is not None and rt.is_cuda:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         xs, info = op.solve(lrhs, restart, aug, max_it=300, rtol=rtol)
+        if prof is not None and rt.is_cuda:
+            ev1.record()
+            keys = K.ReducedOperator.KEYS_INEQ if ineq else K.ReducedOperator.KEYS_EQ
+            fl = 0.0
+            for key in keys:
+                s_, S_ = sys_.A[key].shape[0], sys_.A[key].shape[3]
+                fl += (2.0 * r * n * R * R * S_ + 2.0 * r * R * s_ * n * n * S_ + 2.0 * r * n * R * r * s_) * \
+                      (2 if key == (0, 1) else 1)
+            prof.append((ev0, ev1, info, dict(nv=nred * m, mv_flops=fl, restart=restart, r=r, R=R)))
         if stats is not None:
-            stats.append((xs, info, nred * m))
+            stats["lgmres"].append(info)
         sol = rt.empty(r, b, n, R)
         for q, j in enumerate(src):
             if use_prev:
