@@ -181,6 +181,8 @@ def main():
     ap.add_argument("--workload", default="maxcut_10", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--driver", default="native", choices=["native", "python"],
+                    help="native = C++ sweep driver inside libttipm_b200 (default); python = same kernels driven from Python")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -200,14 +202,15 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from ttipm_b200 import get_runtime, kernels as K
-    from ttipm_b200.amen import DeviceBlockAmen
+    from ttipm_b200.amen import DeviceBlockAmen, NativeBlockAmen
     import tt_oracle as O
     rt = get_runtime()
     systems = load_systems(args.workload)
 
     # ---- problem set-up (not timed): upload operator blocks / rhs, retract warm starts like the reference ----
     def make(g):
-        solver = DeviceBlockAmen(g["A"], g["aliases"], g["transposes"], g["b"], g["ineq"], rt=rt)
+        cls = NativeBlockAmen if args.driver == "native" else DeviceBlockAmen
+        solver = cls(g["A"], g["aliases"], g["transposes"], g["b"], g["ineq"], rt=rt)
         return solver
 
     def host_x0(g):
@@ -222,6 +225,8 @@ def main():
     for g in systems:
         rng_after.append(g["rng_state"])
 
+    native = args.driver == "native"
+
     def device_pass(profile=None):
         """value leg: everything resident, only the sweeps are timed."""
         states = []
@@ -229,6 +234,8 @@ def main():
         for g, x0 in zip(systems, x0s):
             np.random.set_state(g["rng_state"])
             s = make(g)
+            if profile is not None:
+                s.stats["profile"] = profile
             st = s.prepare([c.copy() for c in x0] if x0 is not None else None, 2, True)
             solvers.append(s)
             states.append(st)
@@ -238,12 +245,15 @@ def main():
         e0.record()
         outs = []
         for g, s, st in zip(systems, solvers, states):
-            if profile is not None:
-                s.stats["profile"] = profile
             outs.append(s.run(st, g["termination_tol"], g["rank_restriction"], g["eps"], g["inner_m"]))
         e1.record()
         torch.cuda.synchronize(dev)
-        return e0.elapsed_time(e1) * 1e-3, rt.launches - l0, solvers, outs
+        nl = rt.launches - l0
+        if native:
+            for s in solvers:
+                s.fetch()                      # after the timed region: statistics (+ the result) of the run
+                nl += int(s.native_stats["launches"])
+        return e0.elapsed_time(e1) * 1e-3, nl, solvers, outs
 
     def e2e_pass():
         """e2e leg: NumPy cores in, NumPy cores out, H2D/D2H inside the timed region."""
@@ -297,6 +307,12 @@ def main():
     t_prof, _, solvers, outs = device_pass(profile=prof)
     lg_time = lg_flops = 0.0
     lg_calls = lg_its = 0
+    if native:
+        for s in solvers:
+            lg_time += s.native_stats["krylov_seconds"]
+            lg_flops += s.native_stats["krylov_flops"]
+            lg_calls += int(s.native_stats["krylov_solves"])
+            lg_its += int(s.native_stats["krylov_its"])
     for ev0, ev1, info, shape in prof:
         ms = ev0.elapsed_time(ev1)
         inf = rt.to_host(info)
@@ -324,6 +340,7 @@ def main():
             "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][1]}; {nsys} KKT systems traced from the "
                                    "reference IPM run (block AMEn solve of each = 1 step)",
                        "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "driver": args.driver,
                        "l2": "working set << L2 by construction of the problem (TT cores of KBs); every step re-uploads "
                              "nothing and re-runs all kernels, no result is cached between steps"},
             "e2e": {"value": e2e_mean / nsys, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},

@@ -168,6 +168,31 @@ int ttipm_embed(const double* in, double* out, int r, int R, int q, int mode, vo
 int ttipm_scale2d(const double* in, int64_t in_rs, int64_t in_cs, int rows, int cols, const double* s, int axis,
                   int divide, double* out, void* stream);
 
+/* ---- native sweep driver: one object = one block AMEn solve of a KKT system -------------------------
+ * Replaces tt_block_amen / _bck_sweep / _fwd_sweep (reference src/tt_als.py:277-670) together with the local
+ * solvers _ipm_local_solver[_ineq] (reference src/tt_ipm.py:183-401).  The host passes the operator blocks,
+ * right-hand sides, the warm start and the (host-RNG generated) residual train once; run() executes every
+ * sweep from C++ on `stream` and only synchronises for the scalars the reference's control flow needs.
+ * All `*_host` pointers are HOST memory (NumPy buffers); cores are row-major. */
+typedef struct ttipm_amen ttipm_amen;
+ttipm_amen* ttipm_amen_create(int d, int block_size, int ineq, void* stream);
+void ttipm_amen_destroy(ttipm_amen* h);
+int ttipm_amen_set_block(ttipm_amen* h, int i, int j, int k, const double* core_host, int s, int n, int S);
+int ttipm_amen_add_alias(ttipm_amen* h, int i, int j, int p, int t, int is_transpose);
+int ttipm_amen_set_rhs(ttipm_amen* h, int i, int k, const double* core_host, int rb, int n, int rb2);
+/* which: 0 = solution train, 1 = residual train; nb = 0 for an ordinary core (r, n, R), else the block core */
+int ttipm_amen_set_core(ttipm_amen* h, int which, int k, const double* core_host, int r, int nb, int n, int R);
+int ttipm_amen_run(ttipm_amen* h, double term_tol, int r_max, double eps, int nswp, int kick_rank, int use_amen,
+                   int direction, double* final_res, int* sweeps);
+int ttipm_amen_core_shape(ttipm_amen* h, int k, int32_t* dims /* r, nb|0, n, R */);
+int ttipm_amen_get_core(ttipm_amen* h, int k, double* dst_host);
+/* profile != 0: time every Krylov-kernel launch of the next run() with CUDA events (read back through stats) */
+int ttipm_amen_set_profile(ttipm_amen* h, int on);
+/* stats[12] = sweeps, local solves, dense solves, Krylov solves, Krylov inner steps, Krylov matvecs, kernel
+ * launches, host syncs, peak device bytes, trace rows, seconds inside the Krylov kernel (profiling runs only), its
+ * algorithmic flops; trace: 5 doubles (swp, k, res_old, res_new, r*R) per solve */
+int ttipm_amen_stats(ttipm_amen* h, double* stats, double* trace, int max_trace_rows);
+
 #ifdef __cplusplus
 }
 #endif

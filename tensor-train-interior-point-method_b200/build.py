@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libttipm_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
-         "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-lcublas", "-lcusolver"]
 
 
 def sources():

@@ -1,0 +1,1232 @@
+// Native sweep driver: the whole block AMEn solve of one KKT system behind ONE C-ABI object.
+//
+// Mirrors tt_block_amen / _bck_sweep / _fwd_sweep (reference src/tt_als.py:277-670) and the two local
+// solvers (reference src/tt_ipm.py:183-401).  The control flow is the reference's; every numerical step is
+// a kernel of this library launched back-to-back on one stream from C++, device buffers come from the
+// stream-ordered allocator, and the host only waits for the handful of scalars the reference branches on
+// (residual norms, singular values, truncation norms) through a pinned staging buffer.  The Python layer
+// (ttipm_b200.amen) only uploads the operands, makes the reference's NumPy RNG draws and fetches the result.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include "tensor.h"
+
+#ifndef TTIPM_EMU
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+#endif
+
+namespace ttipm {
+namespace drv {
+
+// ---------------------------------------------------------------------------------------------------
+// memory and transfers
+// ---------------------------------------------------------------------------------------------------
+void* dev_alloc(Ctx& c, size_t bytes) {
+    void* p = nullptr;
+#ifdef TTIPM_EMU
+    p = malloc(bytes ? bytes : 8);
+#else
+    if (cudaMallocAsync(&p, bytes ? bytes : 8, c.st) != cudaSuccess) throw DriverError(91, "device allocation failed");
+#endif
+    c.bytes_live += bytes;
+    if (c.bytes_live > c.bytes_peak) c.bytes_peak = c.bytes_live;
+    return p;
+}
+void dev_free(Ctx& c, void* p, size_t bytes) {
+#ifdef TTIPM_EMU
+    free(p);
+#else
+    cudaFreeAsync(p, c.st);
+#endif
+    c.bytes_live -= bytes;
+}
+static void ensure_pinned(Ctx& c, size_t n) {
+    if (c.pinned_cap >= n) return;
+#ifdef TTIPM_EMU
+    free(c.pinned);
+    c.pinned = (double*)malloc(n * sizeof(double));
+#else
+    if (c.pinned) cudaFreeHost(c.pinned);
+    if (cudaMallocHost((void**)&c.pinned, n * sizeof(double)) != cudaSuccess) throw DriverError(91, "pinned allocation failed");
+#endif
+    c.pinned_cap = n;
+}
+void to_host(Ctx& c, const double* dev, size_t n, double* host) {
+#ifdef TTIPM_EMU
+    memcpy(host, dev, n * sizeof(double));
+#else
+    ensure_pinned(c, n);
+    cudaMemcpyAsync(c.pinned, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c.st);
+    if (cudaStreamSynchronize(c.st) != cudaSuccess) throw DriverError(92, std::string("stream sync failed: ") +
+                                                                           cudaGetErrorString(cudaGetLastError()));
+    memcpy(host, c.pinned, n * sizeof(double));
+#endif
+    c.syncs++;
+}
+void from_host(Ctx& c, const double* host, size_t n, double* dev) {
+#ifdef TTIPM_EMU
+    memcpy(dev, host, n * sizeof(double));
+#else
+    cudaMemcpyAsync(dev, host, n * sizeof(double), cudaMemcpyHostToDevice, c.st);
+    cudaStreamSynchronize(c.st);       // the host buffer is pageable and may be released by the caller
+#endif
+}
+void dev_to_dev(Ctx& c, const double* src, size_t n, double* dst) {
+    if (dev_copy(dst, src, n * sizeof(double), c.st)) throw DriverError(92, "device copy failed");
+}
+static std::vector<double> read_vec(Ctx& c, const Tensor& t) {
+    std::vector<double> h((size_t)t.numel());
+    to_host(c, t.p, h.size(), h.data());
+    return h;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel wrappers (same roles as ttipm_b200/kernels.py)
+// ---------------------------------------------------------------------------------------------------
+struct Terms {
+    std::vector<ttipm_term> v;
+    void add(const Tensor& P1, const Tensor& A, const Tensor& P2, int in_blk, int out_blk, double alpha = 1.0) {
+        ttipm_term t;
+        t.P1 = P1.p; t.A = A.p; t.P2 = P2.p;
+        for (int i = 0; i < 3; ++i) { t.p1_strides[i] = P1.s[i]; t.p2_strides[i] = P2.s[i]; }
+        for (int i = 0; i < 4; ++i) t.a_strides[i] = A.s[i];
+        t.s = (int)A.d[0]; t.S = (int)A.d[3];
+        t.in_block = in_blk; t.out_block = out_blk; t.alpha = alpha;
+        v.push_back(t);
+    }
+};
+
+// x: (r, b, n, R) ["rbnR"] or (r, n, b, R) ["rnbR"], optionally with a leading batch axis
+static Tensor block_matvec(Ctx& c, const Terms& tl, const Tensor& x, bool rnbR, int nb_out, long l, long L,
+                           const Tensor* sub, double y_scale, double sub_scale, Tensor* sumsq) {
+    const bool batched = x.nd == 5;
+    const int o = batched ? 1 : 0;
+    const long B = batched ? x.d[0] : 1;
+    const long r = x.d[o], n = rnbR ? x.d[o + 1] : x.d[o + 2], R = x.d[o + 3];
+    const long x_rs = x.s[o], x_ns = rnbR ? x.s[o + 1] : x.s[o + 2], x_bs = rnbR ? x.s[o + 2] : x.s[o + 1];
+    Tensor y = batched ? Tensor::empty(c, {B, l, (long)nb_out, n, L}) : Tensor::empty(c, {l, (long)nb_out, n, L});
+    if (sumsq) *sumsq = Tensor::empty(c, {B, nb_out * L});
+    check_rc(ttipm_block_matvec(tl.v.data(), (int)tl.v.size(), (int)l, (int)L, (int)r, (int)R, (int)n, nb_out, x.p, x_bs,
+                                x_rs, x_ns, batched ? x.s[0] : 0, y.p, n * L, nb_out * n * L, L, l * nb_out * n * L,
+                                y_scale, sub ? sub->p : nullptr, sub_scale, sumsq ? sumsq->p : nullptr, (int)B, c.st),
+             "block_matvec");
+    c.launches++;
+    return y;
+}
+
+static Tensor local_diag_inv(Ctx& c, const Tensor& P1, const Tensor& A, const Tensor& P2) {
+    Terms t;
+    t.add(P1, A, P2, 0, 0);
+    Tensor out = Tensor::empty(c, {P1.d[0], A.d[1], P2.d[0]});
+    check_rc(ttipm_local_diag(t.v.data(), (int)P1.d[0], (int)P2.d[0], (int)A.d[1], 1, out.p, c.st), "local_diag");
+    c.launches++;
+    return out;
+}
+
+static Tensor local_dense(Ctx& c, const Tensor& P1, const Tensor& A, const Tensor& P2) {
+    Terms t;
+    t.add(P1, A, P2, 0, 0);
+    const long l = P1.d[0], r = P1.d[2], L = P2.d[0], R = P2.d[2], n = A.d[1];
+    Tensor out = Tensor::empty(c, {l * n * L, r * n * R});
+    check_rc(ttipm_local_dense(t.v.data(), (int)l, (int)L, (int)r, (int)R, (int)n, out.p, c.st), "local_dense");
+    c.launches++;
+    return out;
+}
+
+static std::vector<Tensor> phi_update(Ctx& c, const std::vector<Tensor>& phis, const std::vector<Tensor>& cores,
+                                      const Tensor& U, const Tensor& V, bool forward) {
+    const size_t n = phis.size();
+    std::vector<ttipm_phi_term> t(n);
+    std::vector<Tensor> outs(n);
+    const long ul = U.d[0], nm = U.d[1], uL = U.d[2], vr = V.d[0], vR = V.d[2];
+    for (size_t q = 0; q < n; ++q) {
+        const long s = cores[q].d[0], S = cores[q].d[3];
+        outs[q] = forward ? Tensor::empty(c, {uL, S, vR}) : Tensor::empty(c, {ul, s, vr});
+        t[q].Phi = phis[q].p; t[q].A = cores[q].p; t[q].out = outs[q].p;
+        for (int i = 0; i < 4; ++i) t[q].a_strides[i] = cores[q].s[i];
+        t[q].s = (int)s; t[q].S = (int)S;
+    }
+    check_rc(ttipm_phi_update(t.data(), (int)n, forward ? 1 : 0, U.p, (int)ul, (int)uL, V.p, (int)vr, (int)vR, (int)nm,
+                              c.st), "phi_update");
+    c.launches++;
+    return outs;
+}
+
+// out (r, nb, n, R) zero-initialised; rows[q] gives the block of term q
+static Tensor rhs_project(Ctx& c, const std::vector<Tensor>& X1, const std::vector<Tensor>& Bc,
+                          const std::vector<Tensor>& X2, const std::vector<int>& rows, long r, int nb, long n, long R) {
+    Tensor out = Tensor::empty(c, {r, (long)nb, n, R});
+    if (dev_memset(out.p, 0, sizeof(double) * (size_t)out.numel(), c.st)) throw DriverError(92, "memset failed");
+    if (rows.empty()) return out;
+    std::vector<ttipm_rhs_term> t(rows.size());
+    for (size_t q = 0; q < rows.size(); ++q) {
+        t[q].Xb1 = X1[q].p; t[q].B = Bc[q].p; t[q].Xb2 = X2[q].p;
+        t[q].out = out.p + rows[q] * out.s[1];
+        t[q].b = (int)Bc[q].d[0]; t[q].Bp = (int)Bc[q].d[2];
+    }
+    check_rc(ttipm_rhs_contract(t.data(), (int)t.size(), 0, nullptr, (int)r, (int)R, (int)n, out.s[0], c.st), "rhs_project");
+    c.launches++;
+    return out;
+}
+
+static std::vector<Tensor> phi_rhs_update(Ctx& c, const std::vector<Tensor>& Xb, const std::vector<Tensor>& Bc,
+                                          const Tensor& core, bool forward) {
+    const size_t n = Bc.size();
+    std::vector<ttipm_rhs_term> t(n);
+    std::vector<Tensor> outs(n);
+    const long r = core.d[0], nm = core.d[1], R = core.d[2];
+    for (size_t q = 0; q < n; ++q) {
+        t[q].B = Bc[q].p; t[q].b = (int)Bc[q].d[0]; t[q].Bp = (int)Bc[q].d[2];
+        if (forward) { outs[q] = Tensor::empty(c, {Bc[q].d[2], R}); t[q].Xb1 = Xb[q].p; t[q].Xb2 = nullptr; }
+        else { outs[q] = Tensor::empty(c, {Bc[q].d[0], r}); t[q].Xb1 = nullptr; t[q].Xb2 = Xb[q].p; }
+        t[q].out = outs[q].p;
+    }
+    if (n) {
+        check_rc(ttipm_rhs_contract(t.data(), (int)n, forward ? 1 : 2, core.p, (int)r, (int)R, (int)nm, 0, c.st),
+                 "phi_rhs_update");
+        c.launches++;
+    }
+    return outs;
+}
+
+// C = A @ B for 2-D strided views or batched 3-D views
+static Tensor gemm(Ctx& c, const Tensor& A, const Tensor& B) {
+    const bool batched = A.nd == 3;
+    const int o = batched ? 1 : 0;
+    const long nb = batched ? A.d[0] : 1, M = A.d[o], K = A.d[o + 1], N = B.d[o + 1];
+    Tensor C = batched ? Tensor::empty(c, {nb, M, N}) : Tensor::empty(c, {M, N});
+    check_rc(ttipm_gemm((int)M, (int)N, (int)K, 1.0, A.p, A.s[o], A.s[o + 1], batched && nb > 1 ? A.s[0] : 0, B.p, B.s[o],
+                        B.s[o + 1], batched && nb > 1 ? B.s[0] : 0, 0.0, C.p, N, 1, M * N, (int)nb, c.st), "gemm");
+    c.launches++;
+    return C;
+}
+
+static void qr(Ctx& c, const Tensor& A, Tensor& Q, Tensor& R) {
+    const long M = A.d[0], N = A.d[1], K = std::min(M, N);
+    Q = Tensor::empty(c, {M, K});
+    R = Tensor::empty(c, {K, N});
+    Tensor ws = Tensor::empty(c, {(long)ttipm_qr_workspace((int)M, (int)N, 1)});
+    check_rc(ttipm_qr(A.p, A.s[0], A.s[1], 0, (int)M, (int)N, Q.p, R.p, ws.p, 1, c.st), "qr");
+    c.launches++;
+}
+
+static void svd_left(Ctx& c, const Tensor& A, Tensor& U, Tensor& S, Tensor& W) {
+    const long M = A.d[0], N = A.d[1], K = std::min(M, N);
+    U = Tensor::empty(c, {M, K});
+    S = Tensor::empty(c, {K});
+    W = Tensor::empty(c, {K, N});
+    Tensor ws = Tensor::empty(c, {(long)ttipm_svd_workspace((int)M, (int)N, 1)});
+    check_rc(ttipm_svd_left(A.p, A.s[0], A.s[1], 0, (int)M, (int)N, U.p, S.p, W.p, ws.p, nullptr, 1, c.st), "svd_left");
+    c.launches++;
+}
+
+// materialised permutation of a contiguous 4-D tensor, optional scaling along an OUTPUT axis
+static Tensor permute4(Ctx& c, const Tensor& x, int p0, int p1, int p2, int p3, const Tensor* scale, int axis, bool divide) {
+    if (!x.contiguous() || x.nd != 4) throw DriverError(90, "permute4 needs a contiguous 4-D tensor");
+    int32_t dims[4] = {(int32_t)x.d[0], (int32_t)x.d[1], (int32_t)x.d[2], (int32_t)x.d[3]};
+    int32_t perm[4] = {p0, p1, p2, p3};
+    Tensor out = Tensor::empty(c, {x.d[p0], x.d[p1], x.d[p2], x.d[p3]});
+    check_rc(ttipm_permute4(x.p, dims, perm, out.p, scale ? scale->p : nullptr, axis, divide ? 2 : 1, c.st), "permute4");
+    c.launches++;
+    return out;
+}
+
+static Tensor block_norms(Ctx& c, const Tensor& x) {
+    Tensor out = Tensor::empty(c, {x.d[1]});
+    check_rc(ttipm_block_norms(x.p, (int)x.d[0], (int)x.d[1], (int)(x.numel() / (x.d[0] * x.d[1])), 1e-10, out.p, c.st),
+             "block_norms");
+    c.launches++;
+    return out;
+}
+
+// (rows, inner, stride) view of a contiguous tensor or an x[:, j]-style slice
+struct Panel { const double* p; long rs; };
+static void panels(const Tensor* ts[], int n, long& rows, long& inner, long rs[]) {
+    const Tensor* first = nullptr;
+    bool all_contig = true;
+    for (int i = 0; i < n; ++i)
+        if (ts[i]) {
+            if (!first) first = ts[i];
+            all_contig = all_contig && ts[i]->contiguous();
+        }
+    if (all_contig) {
+        rows = 1;
+        inner = first->numel();
+        for (int i = 0; i < n; ++i) rs[i] = ts[i] ? inner : 0;
+        return;
+    }
+    rows = first->d[0];
+    inner = first->numel() / rows;
+    for (int i = 0; i < n; ++i) rs[i] = ts[i] ? ts[i]->s[0] : 0;
+}
+
+// out = w .* (alpha a + beta b) + gamma c ; any of b, c, w, out may be null; optional sum-of-squares partials
+static void ewise(Ctx& c, const Tensor& a, double alpha, const Tensor* b, double beta, const Tensor* cc, double gamma,
+                  const Tensor* w, Tensor* out, Tensor* sumsq) {
+    const Tensor* ts[5] = {&a, b, cc, w, out};
+    long rows, inner, rs[5];
+    panels(ts, 5, rows, inner, rs);
+    if (sumsq) *sumsq = Tensor::empty(c, {256});
+    check_rc(ttipm_ewise((int)rows, (int)inner, alpha, a.p, rs[0], beta, b ? b->p : nullptr, rs[1], gamma,
+                         cc ? cc->p : nullptr, rs[2], w ? w->p : nullptr, rs[3], out ? out->p : nullptr, rs[4],
+                         sumsq ? sumsq->p : nullptr, c.st), "ewise");
+    c.launches++;
+}
+
+static Tensor copy2d(Ctx& c, const Tensor& A) {     // contiguous copy of a strided 2-D view
+    Tensor out = Tensor::empty(c, {A.d[0], A.d[1]});
+    check_rc(ttipm_scale2d(A.p, A.s[0], A.s[1], (int)A.d[0], (int)A.d[1], nullptr, 0, 0, out.p, c.st), "copy2d");
+    c.launches++;
+    return out;
+}
+
+static double sum_host(const std::vector<double>& h, size_t a, size_t n) {
+    double t = 0.0;
+    for (size_t i = 0; i < n; ++i) t += h[a + i];
+    return t;
+}
+
+// several partial-sum buffers -> totals with ONE synchronising transfer
+static std::vector<double> host_sums(Ctx& c, const std::vector<const Tensor*>& ts) {
+    size_t tot = 0;
+    for (auto t : ts) tot += (size_t)t->numel();
+    Tensor flat = Tensor::empty(c, {(long)tot});
+    size_t o = 0;
+    for (auto t : ts) {
+        dev_to_dev(c, t->p, (size_t)t->numel(), flat.p + o);
+        o += (size_t)t->numel();
+    }
+    std::vector<double> h = read_vec(c, flat);
+    std::vector<double> out;
+    o = 0;
+    for (auto t : ts) {
+        out.push_back(sum_host(h, o, (size_t)t->numel()));
+        o += (size_t)t->numel();
+    }
+    return out;
+}
+
+static int prune_singular_vals(const std::vector<double>& s, double eps) {   // reference cy_src/tt_ops_cy.pyx:162-177
+    const size_t n = s.size();
+    bool allzero = true;
+    for (double v : s) allzero = allzero && v == 0.0;
+    if (allzero) return 1;
+    std::vector<double> sc(n);
+    double acc = 0.0;
+    for (size_t i = n; i-- > 0;) {
+        acc += fabs(s[i]) * fabs(s[i]);
+        sc[i] = acc;
+    }
+    int R = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (sc[i] < eps * eps) { R = (int)i; break; }
+    R = std::max(R, 1);
+    if (sc[n - 1] > eps * eps) R = (int)n;
+    return R;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dense Schur fallback: cuSOLVER / cuBLAS on row-major device matrices (reference src/tt_ipm.py:196-223, :298-334)
+// ---------------------------------------------------------------------------------------------------
+struct Dense {
+    Ctx& c;
+#ifndef TTIPM_EMU
+    cublasHandle_t blas = nullptr;
+    cusolverDnHandle_t sol = nullptr;
+#endif
+    explicit Dense(Ctx& ctx) : c(ctx) {
+#ifndef TTIPM_EMU
+        if (cublasCreate(&blas) != CUBLAS_STATUS_SUCCESS) throw DriverError(93, "cublasCreate failed");
+        if (cusolverDnCreate(&sol) != CUSOLVER_STATUS_SUCCESS) throw DriverError(93, "cusolverDnCreate failed");
+        cublasSetStream(blas, c.st);
+        cusolverDnSetStream(sol, c.st);
+#endif
+    }
+    ~Dense() {
+#ifndef TTIPM_EMU
+        if (sol) cusolverDnDestroy(sol);
+        if (blas) cublasDestroy(blas);
+#endif
+    }
+    // C (M x N) = alpha * op(A) op(B) + beta * C, all row-major contiguous
+    void gemm(bool ta, bool tb, long M, long N, long K, double alpha, const double* A, const double* B, double beta, double* C) {
+#ifdef TTIPM_EMU
+        std::vector<double> out((size_t)(M * N));
+        for (long i = 0; i < M; ++i)
+            for (long j = 0; j < N; ++j) {
+                double acc = 0.0;
+                for (long k = 0; k < K; ++k) acc += (ta ? A[k * M + i] : A[i * K + k]) * (tb ? B[j * K + k] : B[k * N + j]);
+                out[i * N + j] = alpha * acc + (beta != 0.0 ? beta * C[i * N + j] : 0.0);
+            }
+        memcpy(C, out.data(), out.size() * sizeof(double));
+#else
+        // row-major C = A B  <=>  column-major C^T = B^T A^T
+        const long lda = ta ? M : K, ldb = tb ? K : N;
+        if (cublasDgemm(blas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)N, (int)M, (int)K, &alpha,
+                        B, (int)ldb, A, (int)lda, &beta, C, (int)N) != CUBLAS_STATUS_SUCCESS)
+            throw DriverError(93, "cublasDgemm failed");
+#endif
+        c.launches++;
+    }
+    // in-place Cholesky of a symmetric row-major matrix: lower factor in the lower triangle; false if not SPD
+    bool cholesky(double* A, long m) {
+#ifdef TTIPM_EMU
+        for (long j = 0; j < m; ++j) {
+            double d = A[j * m + j];
+            for (long k = 0; k < j; ++k) d -= A[j * m + k] * A[j * m + k];
+            if (!(d > 0.0)) return false;
+            d = sqrt(d);
+            A[j * m + j] = d;
+            for (long i = j + 1; i < m; ++i) {
+                double v = A[i * m + j];
+                for (long k = 0; k < j; ++k) v -= A[i * m + k] * A[j * m + k];
+                A[i * m + j] = v / d;
+            }
+        }
+        return true;
+#else
+        int lwork = 0;
+        cusolverDnDpotrf_bufferSize(sol, CUBLAS_FILL_MODE_UPPER, (int)m, A, (int)m, &lwork);
+        Tensor work = Tensor::empty(c, {(long)lwork + 2});
+        int* info = (int*)(work.p + lwork);
+        if (cusolverDnDpotrf(sol, CUBLAS_FILL_MODE_UPPER, (int)m, A, (int)m, work.p, lwork, info) != CUSOLVER_STATUS_SUCCESS)
+            throw DriverError(93, "potrf failed");
+        double h;
+        to_host(c, work.p + lwork, 1, &h);
+        int hi;
+        memcpy(&hi, &h, sizeof(int));
+        c.launches++;
+        return hi == 0;
+#endif
+    }
+    // X = (L L^T)^{-1} B in place, B row-major (m x k)
+    void chol_solve(const double* Lc, long m, double* B, long k) {
+#ifdef TTIPM_EMU
+        for (long col = 0; col < k; ++col) {
+            for (long i = 0; i < m; ++i) {
+                double v = B[i * k + col];
+                for (long j = 0; j < i; ++j) v -= Lc[i * m + j] * B[j * k + col];
+                B[i * k + col] = v / Lc[i * m + i];
+            }
+            for (long i = m; i-- > 0;) {
+                double v = B[i * k + col];
+                for (long j = i + 1; j < m; ++j) v -= Lc[j * m + i] * B[j * k + col];
+                B[i * k + col] = v / Lc[i * m + i];
+            }
+        }
+#else
+        // column-major view: B^T (k x m), factor U = L^T upper with A = U^T U; solve X^T U^T U = B^T from the right
+        const double one = 1.0;
+        if (cublasDtrsm(blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)k, (int)m,
+                        &one, Lc, (int)m, B, (int)k) != CUBLAS_STATUS_SUCCESS ||
+            cublasDtrsm(blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)k, (int)m,
+                        &one, Lc, (int)m, B, (int)k) != CUBLAS_STATUS_SUCCESS)
+            throw DriverError(93, "trsm failed");
+        c.launches += 2;
+#endif
+    }
+    // LU factorisation (partial pivoting) of a row-major matrix in place; piv has m ints (stored in doubles)
+    struct LU { Tensor a; Tensor piv; long m; };
+    LU lu_factor(const Tensor& A, long m) {
+        LU f;
+        f.m = m;
+        f.a = Tensor::empty(c, {m, m});
+        dev_to_dev(c, A.p, (size_t)(m * m), f.a.p);
+        f.piv = Tensor::empty(c, {m + 2});
+#ifdef TTIPM_EMU
+        int* piv = (int*)f.piv.p;
+        double* a = f.a.p;           // factor the row-major matrix directly (row pivoting)
+        for (long k = 0; k < m; ++k) {
+            long best = k;
+            for (long i = k + 1; i < m; ++i)
+                if (fabs(a[i * m + k]) > fabs(a[best * m + k])) best = i;
+            piv[k] = (int)best;
+            if (best != k)
+                for (long j = 0; j < m; ++j) std::swap(a[k * m + j], a[best * m + j]);
+            for (long i = k + 1; i < m; ++i) {
+                a[i * m + k] /= a[k * m + k];
+                for (long j = k + 1; j < m; ++j) a[i * m + j] -= a[i * m + k] * a[k * m + j];
+            }
+        }
+#else
+        int lwork = 0;
+        cusolverDnDgetrf_bufferSize(sol, (int)m, (int)m, f.a.p, (int)m, &lwork);
+        Tensor work = Tensor::empty(c, {(long)lwork + 2});
+        int* info = (int*)(work.p + lwork);
+        if (cusolverDnDgetrf(sol, (int)m, (int)m, f.a.p, (int)m, work.p, (int*)f.piv.p, info) != CUSOLVER_STATUS_SUCCESS)
+            throw DriverError(93, "getrf failed");
+        c.launches++;
+#endif
+        return f;
+    }
+    // X = A^{-1} B for row-major B (m x k); returns a new row-major tensor
+    Tensor lu_solve(const LU& f, const Tensor& B, long k) {
+        const long m = f.m;
+#ifdef TTIPM_EMU
+        Tensor X = Tensor::empty(c, {m, k});
+        memcpy(X.p, B.p, sizeof(double) * (size_t)(m * k));
+        const int* piv = (const int*)f.piv.p;
+        const double* a = f.a.p;
+        for (long col = 0; col < k; ++col) {
+            for (long i = 0; i < m; ++i)
+                if (piv[i] != i) std::swap(X.p[i * k + col], X.p[piv[i] * k + col]);
+            for (long i = 0; i < m; ++i)
+                for (long j = 0; j < i; ++j) X.p[i * k + col] -= a[i * m + j] * X.p[j * k + col];
+            for (long i = m; i-- > 0;) {
+                for (long j = i + 1; j < m; ++j) X.p[i * k + col] -= a[i * m + j] * X.p[j * k + col];
+                X.p[i * k + col] /= a[i * m + i];
+            }
+        }
+        return X;
+#else
+        // memory of row-major A is column-major A^T =: C (factored); A X = B <=> C^T X = B; getrs wants column-major
+        // right-hand sides, i.e. B^T in row-major memory, and returns X^T the same way
+        Tensor Bt = k == 1 ? Tensor::empty(c, {m, 1}) : copy2d(c, B.t2());
+        if (k == 1) dev_to_dev(c, B.p, (size_t)m, Bt.p);
+        Tensor info = Tensor::empty(c, {2});
+        if (cusolverDnDgetrs(sol, CUBLAS_OP_T, (int)m, (int)k, f.a.p, (int)m, (const int*)f.piv.p, Bt.p, (int)m,
+                             (int*)info.p) != CUSOLVER_STATUS_SUCCESS)
+            throw DriverError(93, "getrs failed");
+        c.launches++;
+        if (k == 1) return Bt.reshape({m, 1});
+        Tensor Xt = Bt.reshape({k, m});
+        return copy2d(c, Xt.t2());
+#endif
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// the solver object
+// ---------------------------------------------------------------------------------------------------
+struct Amen {
+    Ctx c;
+    int d = 0, bs = 0;
+    bool ineq = false;
+    std::map<Key, std::vector<Tensor>> A;      // operator cores (s, n, n, S)
+    std::map<Key, Key> aliases, transposes;
+    std::map<int, std::vector<Tensor>> b;      // rhs cores (rb, n, rb')
+    std::vector<Tensor> x, z;
+    std::vector<KeyMap> XAX, ZAX;
+    std::vector<RowMap> Xb, Zb;
+    std::vector<long> rx, rz, N;
+    bool amen = true;
+    int kick_rank = 2, r_max = 100;
+    double eps = 1e-12, trunc_tol = 0.0;
+    bool direct_solve_failure = false;
+    int sweeps = 0;
+    long local_solves = 0, lgmres_its = 0, lgmres_matvecs = 0, lgmres_calls = 0, dense_solves = 0;
+    std::vector<double> trace;                 // (swp, k, res_old, res_new, r*R) per local solve
+    std::unique_ptr<Dense> dense;
+    std::vector<Tensor> lg_infos;              // device info blocks of the Krylov solves (read lazily)
+    struct LgProf {
+#ifndef TTIPM_EMU
+        cudaEvent_t e0, e1;
+#endif
+        double mv_flops, nv;
+        int restart;
+    };
+    std::vector<LgProf> lg_prof;               // one record per Krylov solve (same order as lg_infos)
+    bool profile = false;
+    std::string error;
+
+    Tensor ones(std::initializer_list<long> dims) {
+        Tensor t = Tensor::empty(c, dims);
+        std::vector<double> h((size_t)t.numel(), 1.0);
+        from_host(c, h.data(), h.size(), t.p);
+        return t;
+    }
+
+    // ---- term lists ------------------------------------------------------------------------------
+    Terms full_terms(int k) {
+        Terms tl;
+        for (auto& kv : A) {
+            const Key key = kv.first;
+            const Tensor& Ak = kv.second[k];
+            const Tensor &P1 = XAX[k].at(key), &P2 = XAX[k + 1].at(key);
+            tl.add(P1, Ak, P2, key.second, key.first);
+            auto tr = transposes.find(key);
+            if (tr != transposes.end())
+                tl.add(P1.permute({2, 1, 0}), Ak.permute({0, 2, 1, 3}), P2.permute({2, 1, 0}), tr->second.second, tr->second.first);
+            auto al = aliases.find(key);
+            if (al != aliases.end()) tl.add(P1, Ak, P2, al->second.second, al->second.first);
+        }
+        return tl;
+    }
+    // compressed_/lcompressed_/rcompressed_block_local_product (reference src/tt_als.py:202-238)
+    Terms mixed_terms(int k, const KeyMap& left, const KeyMap& right, bool left_is_z, bool right_is_z) {
+        Terms tl;
+        for (auto& kv : A) {
+            const Key key = kv.first;
+            const Tensor& Ak = kv.second[k];
+            tl.add(left.at(key), Ak, right.at(key), key.second, key.first);
+            auto tr = transposes.find(key);
+            if (tr != transposes.end()) {
+                const Key pt = tr->second;
+                Tensor Pl = left_is_z ? left.at(pt) : left.at(key).permute({2, 1, 0});
+                Tensor Pr = right_is_z ? right.at(pt) : right.at(key).permute({2, 1, 0});
+                tl.add(Pl, Ak.permute({0, 2, 1, 3}), Pr, pt.second, pt.first);
+            }
+            auto al = aliases.find(key);
+            if (al != aliases.end()) tl.add(left.at(key), Ak, right.at(key), al->second.second, al->second.first);
+        }
+        return tl;
+    }
+    Tensor rhs_block(int k, const RowMap& Xl, const RowMap& Xr, long r, long n, long R) {
+        std::vector<Tensor> X1, Bc, X2;
+        std::vector<int> rows;
+        for (auto& kv : b) {
+            rows.push_back(kv.first);
+            X1.push_back(Xl.at(kv.first));
+            Bc.push_back(kv.second[k]);
+            X2.push_back(Xr.at(kv.first));
+        }
+        return rhs_project(c, X1, Bc, X2, rows, r, bs, n, R);
+    }
+    Tensor apply_block(const Tensor& P1, const Tensor& Ak, const Tensor& P2, const Tensor& v3) {   // v3: (r, n, R)
+        Terms tl;
+        tl.add(P1, Ak, P2, 0, 0);
+        Tensor x4 = v3.reshape({v3.d[0], 1, v3.d[1], v3.d[2]});
+        Tensor y = block_matvec(c, tl, x4, false, 1, P1.d[0], P2.d[0], nullptr, 1.0, 0.0, nullptr);
+        return y.reshape({P1.d[0], v3.d[1], P2.d[0]});
+    }
+
+    // ---- local solver (reference src/tt_ipm.py:183-401) ---------------------------------------------------
+    struct LocalOut { Tensor sol, rhs; double res_old, res_new, norm_rhs; };
+
+    Tensor contiguous3(const Tensor& v) {          // x[:, j] slice -> contiguous (r, n, R)
+        Tensor out = Tensor::empty(c, {v.d[0], v.d[1], v.d[2]});
+        ewise(c, v, 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, &out, nullptr);
+        return out;
+    }
+
+    Tensor dense_solve(int k, const Tensor& rhs, const Tensor& inv_I, long r, long n, long R) {
+        if (!dense) dense.reset(new Dense(c));
+        Dense& D = *dense;
+        const long m = r * n * R;
+        auto blk = [&](int i, int j) { return local_dense(c, XAX[k].at({i, j}), A.at({i, j})[k], XAX[k + 1].at({i, j})); };
+        auto col = [&](int i) { return contiguous3(rhs.select(1, i)).reshape({m, 1}); };
+        auto scale_cols = [&](const Tensor& M) {          // M * inv_I[None, :]
+            Tensor out = Tensor::empty(c, {m, m});
+            check_rc(ttipm_scale2d(M.p, m, 1, (int)m, (int)m, inv_I.p, 1, 0, out.p, c.st), "scale2d");
+            c.launches++;
+            return out;
+        };
+        auto axpy = [&](const Tensor& a, double beta, const Tensor& bb) {   // a + beta * bb (new tensor)
+            Tensor out = Tensor::empty(c, {a.d[0], a.d[1]});
+            ewise(c, a, 1.0, &bb, beta, nullptr, 0.0, nullptr, &out, nullptr);
+            return out;
+        };
+        auto mm = [&](const Tensor& X, const Tensor& Y, bool ty = false) {
+            const long M = X.d[0], K = X.d[1], N = ty ? Y.d[0] : Y.d[1];
+            Tensor out = Tensor::empty(c, {M, N});
+            D.gemm(false, ty, M, N, K, 1.0, X.p, Y.p, 0.0, out.p);
+            return out;
+        };
+        auto add_diag = [&](Tensor& M) {
+            Tensor e = Tensor::empty(c, {m});
+            std::vector<double> h((size_t)m, 1e-11);
+            from_host(c, h.data(), h.size(), e.p);
+            // diag += 1e-11 through the strided panel form (rows = m, inner = 1)
+            check_rc(ttipm_ewise((int)m, 1, 1.0, M.p, m + 1, 1.0, e.p, 1, 0.0, nullptr, 0, nullptr, 0, M.p, m + 1, nullptr, c.st),
+                     "diag shift");
+            c.launches++;
+        };
+        Tensor Lc = blk(2, 1);
+        if (!D.cholesky(Lc.p, m)) throw DriverError(94, "local L_Z block is not positive definite");
+        Tensor sol = Tensor::empty(c, {r, (long)bs, n, R});
+        auto put = [&](int j, const Tensor& v) {
+            Tensor dst = sol.select(1, j);
+            Tensor src = v.reshape({r, n, R});
+            ewise(c, src, 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, &dst, nullptr);
+        };
+        const Tensor &P1_01 = XAX[k].at({0, 1}), &A01 = A.at({0, 1})[k], &P2_01 = XAX[k + 1].at({0, 1});
+        auto applyT01 = [&](const Tensor& y3) {
+            return apply_block(P1_01.permute({2, 1, 0}), A01.permute({0, 2, 1, 3}), P2_01.permute({2, 1, 0}), y3);
+        };
+        if (!ineq) {
+            Tensor Rp = col(0), Rd = col(1), Rc = col(2);
+            Tensor LXI = scale_cols(blk(2, 2));
+            Tensor Leq = blk(0, 1);
+            Tensor t1 = axpy(Rc, -1.0, mm(LXI, Rd));
+            D.chol_solve(Lc.p, m, t1.p, 1);
+            Tensor bb = axpy(Rp, -1.0, mm(Leq, t1));
+            Tensor Zm = Tensor::empty(c, {m, m});
+            dev_to_dev(c, LXI.p, (size_t)(m * m), Zm.p);
+            D.chol_solve(Lc.p, m, Zm.p, m);
+            Tensor S = mm(Leq, mm(Zm, Leq, true));
+            Tensor K00 = blk(0, 0);
+            S = axpy(S, 1.0, K00);
+            add_diag(S);
+            Dense::LU f = D.lu_factor(S, m);
+            Tensor y = D.lu_solve(f, bb, 1);
+            put(0, y);
+            Tensor y3 = contiguous3(sol.select(1, 0));
+            Tensor kty = applyT01(y3).reshape({m, 1});
+            Tensor zz = Tensor::empty(c, {m, 1});
+            Tensor invc = inv_I.reshape({m, 1});
+            ewise(c, Rd, 1.0, &kty, -1.0, nullptr, 0.0, &invc, &zz, nullptr);
+            put(2, zz);
+            Tensor z3 = zz.reshape({r, n, R});
+            Tensor k22z = apply_block(XAX[k].at({2, 2}), A.at({2, 2})[k], XAX[k + 1].at({2, 2}), z3).reshape({m, 1});
+            Tensor xx = axpy(Rc, -1.0, k22z);
+            D.chol_solve(Lc.p, m, xx.p, 1);
+            put(1, xx);
+        } else {
+            Tensor Rp = col(0), Rd = col(1), Rc = col(2), Rt = col(3);
+            Tensor LZc = Tensor::empty(c, {m, 1});
+            dev_to_dev(c, Rc.p, (size_t)m, LZc.p);
+            D.chol_solve(Lc.p, m, LZc.p, 1);
+            Tensor LZX = blk(2, 2);
+            D.chol_solve(Lc.p, m, LZX.p, m);
+            Tensor LZXI = scale_cols(LZX);
+            Tensor Leq = blk(0, 1), Top = blk(3, 1);
+            Tensor w = axpy(LZc, -1.0, mm(LZXI, Rd));
+            Tensor u = axpy(Rp, -1.0, mm(Leq, w));
+            Tensor v = axpy(Rt, -1.0, mm(Top, w));
+            Tensor Am = axpy(blk(0, 0), 1.0, mm(mm(Leq, LZXI), Leq, true));
+            Tensor Dm = axpy(blk(3, 3), 1.0, mm(Top, LZX));
+            add_diag(Dm);
+            Tensor TopS = mm(mm(Top, LZXI), Leq, true);
+            Tensor LeqS = mm(Leq, LZX);
+            Dense::LU fD = D.lu_factor(Dm, m);
+            Tensor rhs_l = axpy(u, -1.0, mm(LeqS, D.lu_solve(fD, v, 1)));
+            Tensor lhs_l = axpy(Am, -1.0, mm(LeqS, D.lu_solve(fD, TopS, m)));
+            Dense::LU fl = D.lu_factor(lhs_l, m);
+            Tensor y = D.lu_solve(fl, rhs_l, 1);
+            put(0, y);
+            Tensor tt = D.lu_solve(fD, axpy(v, -1.0, mm(TopS, y)), 1);
+            put(3, tt);
+            Tensor y3 = contiguous3(sol.select(1, 0));
+            Tensor kty = applyT01(y3).reshape({m, 1});
+            Tensor zz = Tensor::empty(c, {m, 1});
+            Tensor invc = inv_I.reshape({m, 1});
+            ewise(c, Rd, 1.0, &kty, -1.0, &tt, -1.0, &invc, &zz, nullptr);
+            put(2, zz);
+            Tensor z3 = zz.reshape({r, n, R});
+            Tensor k22z = apply_block(XAX[k].at({2, 2}), A.at({2, 2})[k], XAX[k + 1].at({2, 2}), z3).reshape({m, 1});
+            Tensor xx = axpy(Rc, -1.0, k22z);
+            D.chol_solve(Lc.p, m, xx.p, 1);
+            put(1, xx);
+        }
+        dense_solves++;
+        return sol;
+    }
+
+    LocalOut solve_local(int k, const Tensor& prev, int size_limit, bool dense_ok, const Terms& full) {
+        const long r = prev.d[0], n = prev.d[2], R = prev.d[3], m = r * n * R;
+        const double rtol = 1e-5;
+        LocalOut o;
+        o.rhs = rhs_block(k, Xb[k], Xb[k + 1], r, n, R);
+        Tensor rhs_ss, res_ss;
+        ewise(c, o.rhs, 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, nullptr, &rhs_ss);
+        Tensor inv_I = local_diag_inv(c, XAX[k].at({1, 2}), A.at({1, 2})[k], XAX[k + 1].at({1, 2}));
+        block_matvec(c, full, prev, false, bs, r, R, &o.rhs, 1.0, -1.0, &res_ss);
+        std::vector<double> sums = host_sums(c, {&rhs_ss, &res_ss});
+        o.norm_rhs = std::max(sqrt(sums[0]), 1e-10);
+        o.res_old = sqrt(sums[1]) / o.norm_rhs;
+        const double limit = ineq ? 0.95 * size_limit : (double)size_limit;
+        bool dense_now = (sqrt((double)(r * R)) <= limit) && dense_ok && (o.res_old >= rtol);
+        bool direct_fail = !dense_now;
+        if (dense_now) {
+            try {
+                o.sol = dense_solve(k, o.rhs, inv_I, r, n, R);
+            } catch (const DriverError& e) {
+                if (e.code != 94 && e.code != 93) throw;
+                direct_fail = true;
+            }
+        }
+        if (!dense_now || direct_fail) {
+            const int nred = ineq ? 3 : 2;
+            const int src[3] = {0, 1, 3};
+            Terms ops;      // K00, K01, K21, K22, K31, K33
+            const Key keys[6] = {{0, 0}, {0, 1}, {2, 1}, {2, 2}, {3, 1}, {3, 3}};
+            for (int q = 0; q < (ineq ? 6 : 4); ++q) ops.add(XAX[k].at(keys[q]), A.at(keys[q])[k], XAX[k + 1].at(keys[q]), 0, 0);
+            const ttipm_term* T = ops.v.data();
+            const int restart = (int)std::min<long>(m, 100), aug = std::max(restart / 10, 3);
+            Tensor ws = Tensor::empty(c, {(long)ttipm_lgmres_workspace(ineq, (int)r, (int)R, (int)n, restart, aug)});
+            auto lg = [&](const Tensor& in, bool apply_only, Tensor* info) {
+                Tensor out = Tensor::empty(c, {(long)nred, r, n, R});
+                check_rc(ttipm_local_lgmres(ineq, T + 0, T + 1, T + 2, T + 3, ineq ? T + 4 : nullptr, ineq ? T + 5 : nullptr,
+                                            inv_I.p, (int)r, (int)R, (int)n, in.p, out.p, ws.p, ws.numel(), restart, aug, 300,
+                                            rtol, apply_only ? 1 : 0, 0, info ? info->p : nullptr, c.st), "local_lgmres");
+                c.launches++;
+                return out;
+            };
+            Tensor lrhs = Tensor::empty(c, {(long)nred, r, n, R});
+            Tensor l0 = lrhs.select(0, 0), l1 = lrhs.select(0, 1);
+            ewise(c, o.rhs.select(1, 0), 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, &l0, nullptr);
+            Tensor t = Tensor::empty(c, {r, n, R});
+            ewise(c, o.rhs.select(1, 1), 1.0, nullptr, 0.0, nullptr, 0.0, &inv_I, &t, nullptr);
+            Tensor k22t = apply_block(XAX[k].at({2, 2}), A.at({2, 2})[k], XAX[k + 1].at({2, 2}), t);
+            ewise(c, o.rhs.select(1, 2), 1.0, &k22t, -1.0, nullptr, 0.0, nullptr, &l1, nullptr);
+            if (ineq) {
+                Tensor l2 = lrhs.select(0, 2);
+                ewise(c, o.rhs.select(1, 3), 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, &l2, nullptr);
+            }
+            Tensor prev_red = Tensor::empty(c, {(long)nred, r, n, R});
+            for (int q = 0; q < nred; ++q) {
+                Tensor dst = prev_red.select(0, q);
+                ewise(c, prev.select(1, src[q]), 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, &dst, nullptr);
+            }
+            Tensor lvec = lg(prev_red, true, nullptr);
+            Tensor n0, n1, diff = Tensor::empty(c, {(long)nred, r, n, R});
+            ewise(c, lrhs, 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, nullptr, &n0);
+            ewise(c, lrhs, 1.0, &lvec, -1.0, nullptr, 0.0, nullptr, &diff, &n1);
+            std::vector<double> nn = host_sums(c, {&n0, &n1});
+            const bool use_prev = sqrt(nn[1]) < sqrt(nn[0]);
+            Tensor info = Tensor::empty(c, {6});
+            LgProf pr;
+            pr.nv = (double)nred * m;
+            pr.restart = restart;
+            pr.mv_flops = 0.0;
+            for (int q = 0; q < (ineq ? 6 : 4); ++q) {
+                const double s_ = (double)ops.v[q].s, S_ = (double)ops.v[q].S;
+                const double f = 2.0 * r * n * R * R * S_ + 2.0 * r * R * s_ * n * n * S_ + 2.0 * r * n * R * r * s_;
+                pr.mv_flops += (q == 1 ? 2.0 : 1.0) * f;       // K01 is applied both ways
+            }
+#ifndef TTIPM_EMU
+            if (profile) {
+                cudaEventCreate(&pr.e0);
+                cudaEventCreate(&pr.e1);
+                cudaEventRecord(pr.e0, c.st);
+            }
+#endif
+            Tensor xs = lg(use_prev ? diff : lrhs, false, &info);
+#ifndef TTIPM_EMU
+            if (profile) cudaEventRecord(pr.e1, c.st);
+#endif
+            lg_prof.push_back(pr);
+            lg_infos.push_back(info);
+            lgmres_calls++;
+            o.sol = Tensor::empty(c, {r, (long)bs, n, R});
+            for (int q = 0; q < nred; ++q) {
+                Tensor dst = o.sol.select(1, src[q]);
+                Tensor pv = prev.select(1, src[q]);
+                ewise(c, xs.select(0, q), 1.0, use_prev ? &pv : nullptr, 1.0, nullptr, 0.0, nullptr, &dst, nullptr);
+            }
+            Tensor y3 = contiguous3(o.sol.select(1, 0));
+            Tensor kty = apply_block(XAX[k].at({0, 1}).permute({2, 1, 0}), A.at({0, 1})[k].permute({0, 2, 1, 3}),
+                                     XAX[k + 1].at({0, 1}).permute({2, 1, 0}), y3);
+            Tensor dst = o.sol.select(1, 2);
+            Tensor tcol = ineq ? o.sol.select(1, 3) : Tensor();
+            ewise(c, o.rhs.select(1, 1), 1.0, &kty, -1.0, ineq ? &tcol : nullptr, -1.0, &inv_I, &dst, nullptr);
+        }
+        Tensor new_ss;
+        block_matvec(c, full, o.sol, false, bs, r, R, &o.rhs, 1.0, -1.0, &new_ss);
+        std::vector<double> s2 = host_sums(c, {&new_ss});
+        const double res_new = sqrt(s2[0]) / o.norm_rhs;
+        if (o.res_old < res_new) o.sol = prev;
+        o.res_new = std::min(o.res_old, res_new);
+        direct_solve_failure = direct_fail;
+        local_solves++;
+        return o;
+    }
+
+    // ---- interface updates (reference src/tt_als.py:372-387, :499-514) ---------------------------------------
+    void update_interfaces(int k, bool bck, bool zside) {
+        const int src = bck ? k + 1 : k, dst = bck ? k : k + 1;
+        const Tensor& xk = x[k];
+        std::vector<Tensor> Xs, Bc;
+        std::vector<int> rows;
+        std::vector<Tensor> phis, cores;
+        std::vector<Key> keys;
+        const std::vector<KeyMap>& PH = zside ? ZAX : XAX;
+        for (auto& kv : A) {
+            keys.push_back(kv.first);
+            phis.push_back(PH[src].at(kv.first));
+            cores.push_back(kv.second[k]);
+        }
+        if (zside)
+            for (auto& tr : transposes) {
+                keys.push_back(tr.second);
+                phis.push_back(ZAX[src].at(tr.second));
+                cores.push_back(A.at(tr.first)[k].permute({0, 2, 1, 3}));
+            }
+        const Tensor& left = zside ? z[k] : xk;
+        std::vector<Tensor> outs = phi_update(c, phis, cores, left, xk, !bck);
+        KeyMap nm;
+        for (size_t q = 0; q < keys.size(); ++q) nm[keys[q]] = outs[q];
+        (zside ? ZAX : XAX)[dst] = nm;
+        const std::vector<RowMap>& XB = zside ? Zb : Xb;
+        for (auto& kv : b) {
+            rows.push_back(kv.first);
+            Xs.push_back(XB[src].at(kv.first));
+            Bc.push_back(kv.second[k]);
+        }
+        std::vector<Tensor> ro = phi_rhs_update(c, Xs, Bc, left, !bck);
+        RowMap rm;
+        for (size_t q = 0; q < rows.size(); ++q) rm[rows[q]] = ro[q];
+        (zside ? Zb : Xb)[dst] = rm;
+    }
+
+    // ---- one half sweep --------------------------------------------------------------------------------
+    void sweep(int direction, int swp, bool last, double& local_res, double& local_dx) {
+        const bool bck = direction > 0;
+        local_res = swp == 0 ? INFINITY : 0.0;
+        local_dx = swp == 0 ? INFINITY : 0.0;
+        const bool solving = swp > 0 && !last;
+        for (int step = 0; step < d; ++step) {
+            const int k = bck ? d - 1 - step : step;
+            const bool inner = bck ? k > 0 : k < d - 1;
+            const long n = N[k], r_k = rx[k], R_k = rx[k + 1];
+            Tensor sol, resz, rhs;
+            double r_new = 0.0, norm_rhs = 1.0;
+            Terms full;
+            if (solving) {
+                Tensor prev = x[k];
+                full = full_terms(k);
+                LocalOut lo = solve_local(k, prev, 3 * d, !direct_solve_failure, full);
+                sol = lo.sol; rhs = lo.rhs; r_new = lo.res_new; norm_rhs = lo.norm_rhs;
+                trace.insert(trace.end(), {(double)swp, (double)k, lo.res_old, lo.res_new, (double)(r_k * R_k)});
+                local_res = std::max(local_res, lo.res_old);
+                Tensor dnum, dden;
+                ewise(c, sol, 1.0, &prev, -1.0, nullptr, 0.0, nullptr, nullptr, &dnum);
+                ewise(c, sol, 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, nullptr, &dden);
+                std::vector<double> dd = host_sums(c, {&dnum, &dden});
+                local_dx = std::max(local_dx, sqrt(dd[0]) / sqrt(dd[1]));
+                if (amen) {
+                    Tensor rhsz = rhs_block(k, Zb[k], Zb[k + 1], rz[k], n, rz[k + 1]);
+                    resz = block_matvec(c, mixed_terms(k, ZAX[k], ZAX[k + 1], true, true), sol, false, bs, rz[k], rz[k + 1],
+                                        &rhsz, -1.0, 1.0, nullptr);
+                }
+            } else {
+                sol = x[k];
+                if (amen && !last) resz = z[k];
+            }
+            Tensor scales = block_norms(c, sol);
+            Tensor S, mat, rzm;
+            if (bck) {
+                S = permute4(c, sol, 0, 1, 2, 3, &scales, 1, false);                 // (r, b, n, R)
+                mat = S.reshape({r_k * bs, n * R_k}).t2();                            // (n R, r b) view
+                if (resz.defined()) rzm = resz.reshape({rz[k] * bs, n * rz[k + 1]}).t2();
+            } else {
+                S = permute4(c, sol, 0, 2, 1, 3, &scales, 2, false);                 // (r, n, b, R)
+                mat = S.reshape({r_k * n, bs * R_k});
+                if (resz.defined()) rzm = permute4(c, resz, 0, 2, 1, 3, nullptr, 0, false).reshape({rz[k] * n, bs * rz[k + 1]});
+            }
+            if (!inner) {
+                x[k] = bck ? permute4(c, S, 0, 1, 2, 3, &scales, 1, true) : permute4(c, S, 0, 2, 1, 3, &scales, 1, true);
+                if (amen && !last) z[k] = permute4(c, resz, 0, 1, 2, 3, &scales, 1, true);
+                continue;
+            }
+            Tensor U, Sv, W;
+            svd_left(c, mat, U, Sv, W);
+            std::vector<double> s_host = read_vec(c, Sv);
+            const long Kk = U.d[1];
+            long r;
+            Tensor uk, vk;
+            if (solving) {
+                const double trunc_lim = std::max(2 * trunc_tol, r_new);
+                const long r0 = std::min<long>(prune_singular_vals(s_host, eps), r_max);
+                Tensor sol_r0;
+                if (bck) sol_r0 = gemm(c, W.slice(0, 0, r0).t2(), U.slice(1, 0, r0).t2()).reshape({r_k, (long)bs, n, R_k});
+                else sol_r0 = gemm(c, U.slice(1, 0, r0), W.slice(0, 0, r0)).reshape({r_k, n, (long)bs, R_k});
+                Tensor res = block_matvec(c, full, sol_r0, !bck, bs, r_k, R_k, &rhs, 1.0, -1.0, nullptr);
+                r = r0;
+                if (r0 > 1) {
+                    Tensor terms;
+                    if (bck) terms = gemm(c, W.slice(0, 1, r0).unsqueeze(2), U.slice(1, 1, r0).t2().unsqueeze(1))
+                                         .reshape({r0 - 1, r_k, (long)bs, n, R_k});
+                    else terms = gemm(c, U.slice(1, 1, r0).t2().unsqueeze(2), W.slice(0, 1, r0).unsqueeze(1))
+                                     .reshape({r0 - 1, r_k, n, (long)bs, R_k});
+                    Tensor Y = block_matvec(c, full, terms, !bck, bs, r_k, R_k, nullptr, 1.0, 0.0, nullptr);
+                    Tensor parts = Tensor::empty(c, {r0 - 1, 256});
+                    check_rc(ttipm_trunc_resnorms(res.p, Y.p, (int)(r0 - 1), res.numel(), parts.p, c.st), "trunc_resnorms");
+                    c.launches++;
+                    std::vector<double> ph = read_vec(c, parts);
+                    r = 1;
+                    for (long q = r0 - 1; q >= 1; --q) {
+                        if (sqrt(sum_host(ph, (size_t)(q - 1) * 256, 256)) / norm_rhs > trunc_lim) {
+                            r = q;
+                            break;
+                        }
+                    }
+                }
+                r += 1;
+                r = std::min(r, Kk);
+                uk = U.slice(1, 0, r);
+                vk = W.slice(0, 0, r);
+                if (amen) {
+                    Tensor Uz, Sz, Wz;
+                    long kr;
+                    if (bck) {
+                        Tensor rhsxz = rhs_block(k, Zb[k], Xb[k + 1], rz[k], n, R_k);
+                        Tensor resxz = block_matvec(c, mixed_terms(k, ZAX[k], XAX[k + 1], true, false), sol_r0, false, bs,
+                                                    rz[k], R_k, &rhsxz, -1.0, 1.0, nullptr);
+                        kr = std::min<long>(kick_rank, std::min(rz[k] * bs, n * R_k));
+                        svd_left(c, resxz.reshape({rz[k] * bs, n * R_k}).t2(), Uz, Sz, Wz);
+                    } else {
+                        Tensor sol_r = gemm(c, uk, vk).reshape({r_k, n, (long)bs, R_k});
+                        Tensor rhsxz = rhs_block(k, Xb[k], Zb[k + 1], r_k, n, rz[k + 1]);
+                        Tensor resxz = block_matvec(c, mixed_terms(k, XAX[k], ZAX[k + 1], false, true), sol_r, true, bs, r_k,
+                                                    rz[k + 1], &rhsxz, -1.0, 1.0, nullptr);
+                        kr = std::min<long>(kick_rank, std::min(r_k * n, bs * rz[k + 1]));
+                        svd_left(c, permute4(c, resxz, 0, 2, 1, 3, nullptr, 0, false).reshape({r_k * n, bs * rz[k + 1]}), Uz, Sz, Wz);
+                    }
+                    Tensor cat = Tensor::empty(c, {U.d[0], r + kr});
+                    copy_rows(uk, cat.slice(1, 0, r));
+                    copy_rows(Uz.slice(1, 0, kr), cat.slice(1, r, r + kr));
+                    Tensor Q, Rf;
+                    qr(c, cat, Q, Rf);
+                    vk = gemm(c, Rf.slice(1, 0, r), vk);
+                    uk = Q;
+                    r = uk.d[1];
+                }
+            } else {
+                r = std::min<long>(prune_singular_vals(s_host, eps), r_max);
+                uk = U.slice(1, 0, r);
+                vk = W.slice(0, 0, r);
+            }
+            if (bck) {
+                x[k] = copy2d(c, uk.t2()).reshape({r, n, R_k});
+                Tensor vT = copy2d(c, vk.t2());                                         // (r_k * bs, r)
+                const long a = x[k - 1].d[0], dd = x[k - 1].d[1], cc = x[k - 1].d[2];
+                Tensor G = gemm(c, x[k - 1].reshape({a * dd, cc}), vT.reshape({cc, bs * r})).reshape({a, dd, (long)bs, r});
+                x[k - 1] = permute4(c, G, 0, 2, 1, 3, &scales, 1, true);
+                rx[k] = r;
+            } else {
+                x[k] = copy2d(c, uk).reshape({r_k, n, r});
+                const long Rn = x[k + 1].d[0], dd = x[k + 1].d[1], k2 = x[k + 1].d[2];
+                Tensor vc = vk.contiguous() ? vk : copy2d(c, vk);
+                Tensor G = gemm(c, vc.reshape({r * bs, Rn}), x[k + 1].reshape({Rn, dd * k2}));
+                x[k + 1] = permute4(c, G.reshape({r, (long)bs, dd, k2}), 0, 1, 2, 3, &scales, 1, true);
+                rx[k + 1] = r;
+            }
+            update_interfaces(k, bck, false);
+            if (amen && !last) {
+                const long kr = std::min<long>(kick_rank, std::min(rzm.d[0], rzm.d[1]));
+                Tensor Uz, Sz, Wz;
+                svd_left(c, rzm, Uz, Sz, Wz);
+                if (bck) {
+                    z[k] = copy2d(c, Uz.slice(1, 0, kr).t2()).reshape({kr, n, rz[k + 1]});
+                    Tensor vT = copy2d(c, Wz.slice(0, 0, kr).t2());
+                    const long a = z[k - 1].d[0], dd = z[k - 1].d[1], cc = z[k - 1].d[2];
+                    Tensor G = gemm(c, z[k - 1].reshape({a * dd, cc}), vT.reshape({cc, bs * kr})).reshape({a, dd, (long)bs, kr});
+                    z[k - 1] = permute4(c, G, 0, 2, 1, 3, &scales, 1, true);
+                    rz[k] = kr;
+                } else {
+                    z[k] = copy2d(c, Uz.slice(1, 0, kr)).reshape({rz[k], n, kr});
+                    const long Rn = z[k + 1].d[0], dd = z[k + 1].d[1], k2 = z[k + 1].d[2];
+                    Tensor wc = Wz.slice(0, 0, kr);
+                    Tensor G = gemm(c, wc.reshape({kr * bs, Rn}), z[k + 1].reshape({Rn, dd * k2}));
+                    z[k + 1] = permute4(c, G.reshape({kr, (long)bs, dd, k2}), 0, 1, 2, 3, &scales, 1, true);
+                    rz[k + 1] = kr;
+                }
+                update_interfaces(k, bck, true);
+            }
+        }
+    }
+
+    void copy_rows(const Tensor& src, Tensor dst) {      // 2-D views with unit column stride
+        check_rc(ttipm_ewise((int)src.d[0], (int)src.d[1], 1.0, src.p, src.s[0], 0.0, nullptr, 0, 0.0, nullptr, 0, nullptr, 0,
+                             dst.p, dst.s[0], nullptr, c.st), "copy_rows");
+        c.launches++;
+    }
+
+    // ---- whole solve (reference src/tt_als.py:586-670) -------------------------------------------------------
+    double run(double term_tol, int rmax, double eps_, int nswp, int direction) {
+        r_max = rmax;
+        eps = eps_;
+        trunc_tol = term_tol / sqrt((double)d);
+        direct_solve_failure = false;
+        bool last = false;
+        double final_res = INFINITY;
+        sweeps = 0;
+        for (int swp = 0; swp <= nswp; ++swp) {
+            double local_res, local_dx;
+            sweep(direction, swp, last, local_res, local_dx);
+            sweeps = swp;
+            if (last) break;
+            if (local_res < term_tol || local_dx < eps || swp == nswp - 2) {
+                last = true;
+                final_res = local_res;
+            }
+            direction = -direction;
+        }
+        return final_res;
+    }
+};
+
+}  // namespace drv
+}  // namespace ttipm
+
+using namespace ttipm;
+using namespace ttipm::drv;
+
+struct ttipm_amen {
+    Amen a;
+};
+
+#define TT_TRY(h, ...)                                   \
+    try {                                                \
+        __VA_ARGS__;                                     \
+        return 0;                                        \
+    } catch (const DriverError& e) {                     \
+        (h)->a.error = e.what();                         \
+        return fail(e.code ? e.code : 1, "%s", e.what()); \
+    } catch (const std::exception& e) {                  \
+        (h)->a.error = e.what();                         \
+        return fail(99, "%s", e.what());                 \
+    }
+
+extern "C" ttipm_amen* ttipm_amen_create(int d, int block_size, int ineq, void* stream) {
+    ttipm_amen* h = new ttipm_amen();
+    h->a.c.st = (tt_stream_t)stream;
+    h->a.d = d;
+    h->a.bs = block_size;
+    h->a.ineq = ineq != 0;
+    h->a.x.resize(d);
+    h->a.z.resize(d);
+    h->a.rx.assign(d + 1, 1);
+    h->a.rz.assign(d + 1, 1);
+    h->a.N.assign(d, 4);
+    return h;
+}
+
+extern "C" void ttipm_amen_destroy(ttipm_amen* h) {
+    if (!h) return;
+#ifndef TTIPM_EMU
+    if (h->a.c.pinned) cudaFreeHost(h->a.c.pinned);
+#else
+    free(h->a.c.pinned);
+#endif
+    h->a.c.pinned = nullptr;
+    delete h;
+}
+
+static Tensor upload(Ctx& c, const double* host, std::initializer_list<long> dims) {
+    Tensor t = Tensor::empty(c, dims);
+    from_host(c, host, (size_t)t.numel(), t.p);
+    return t;
+}
+
+extern "C" int ttipm_amen_set_block(ttipm_amen* h, int i, int j, int k, const double* core_host, int s, int n, int S) {
+    TT_TRY(h, {
+        auto& v = h->a.A[{i, j}];
+        if ((int)v.size() != h->a.d) v.resize(h->a.d);
+        v[k] = upload(h->a.c, core_host, {(long)s, (long)n, (long)n, (long)S});
+    });
+}
+
+extern "C" int ttipm_amen_add_alias(ttipm_amen* h, int i, int j, int p, int t, int is_transpose) {
+    TT_TRY(h, { (is_transpose ? h->a.transposes : h->a.aliases)[{i, j}] = {p, t}; });
+}
+
+extern "C" int ttipm_amen_set_rhs(ttipm_amen* h, int i, int k, const double* core_host, int rb, int n, int rb2) {
+    TT_TRY(h, {
+        auto& v = h->a.b[i];
+        if ((int)v.size() != h->a.d) v.resize(h->a.d);
+        v[k] = upload(h->a.c, core_host, {(long)rb, (long)n, (long)rb2});
+    });
+}
+
+// which: 0 = solution train x, 1 = residual train z; nb = 0 for an ordinary core (r, n, R), block size for the block core
+extern "C" int ttipm_amen_set_core(ttipm_amen* h, int which, int k, const double* core_host, int r, int nb, int n, int R) {
+    TT_TRY(h, {
+        Amen& a = h->a;
+        Tensor t = nb > 0 ? upload(a.c, core_host, {(long)r, (long)nb, (long)n, (long)R})
+                          : upload(a.c, core_host, {(long)r, (long)n, (long)R});
+        (which == 0 ? a.x : a.z)[k] = t;
+        (which == 0 ? a.rx : a.rz)[k] = r;
+        (which == 0 ? a.rx : a.rz)[k + 1] = R;
+        a.N[k] = n;
+    });
+}
+
+extern "C" int ttipm_amen_run(ttipm_amen* h, double term_tol, int r_max, double eps, int nswp, int kick_rank, int use_amen,
+                              int direction, double* final_res, int* sweeps) {
+    TT_TRY(h, {
+        Amen& a = h->a;
+        a.amen = use_amen != 0;
+        a.kick_rank = kick_rank;
+        const int d = a.d;
+        a.XAX.assign(d + 1, KeyMap());
+        a.Xb.assign(d + 1, RowMap());
+        a.ZAX.assign(d + 1, KeyMap());
+        a.Zb.assign(d + 1, RowMap());
+        for (auto& kv : a.A) {
+            a.XAX[0][kv.first] = a.ones({1, 1, 1});
+            a.XAX[d][kv.first] = a.ones({1, 1, 1});
+            if (a.amen) {
+                a.ZAX[0][kv.first] = a.ones({1, 1, 1});
+                a.ZAX[d][kv.first] = a.ones({1, 1, 1});
+            }
+        }
+        if (a.amen)
+            for (auto& tr : a.transposes) {
+                a.ZAX[0][tr.second] = a.ones({1, 1, 1});
+                a.ZAX[d][tr.second] = a.ones({1, 1, 1});
+            }
+        for (auto& kv : a.b) {
+            a.Xb[0][kv.first] = a.ones({1, 1});
+            a.Xb[d][kv.first] = a.ones({1, 1});
+            if (a.amen) {
+                a.Zb[0][kv.first] = a.ones({1, 1});
+                a.Zb[d][kv.first] = a.ones({1, 1});
+            }
+        }
+        a.trace.clear();
+        const double res = a.run(term_tol, r_max, eps, nswp, direction);
+        if (final_res) *final_res = res;
+        if (sweeps) *sweeps = a.sweeps;
+    });
+}
+
+// shape of solution core k: dims[0..3] = (r, nb or 0, n, R)
+extern "C" int ttipm_amen_set_profile(ttipm_amen* h, int on) {
+    h->a.profile = on != 0;
+    return 0;
+}
+
+extern "C" int ttipm_amen_core_shape(ttipm_amen* h, int k, int32_t* dims) {
+    TT_TRY(h, {
+        const Tensor& t = h->a.x[k];
+        if (t.nd == 4) { dims[0] = (int)t.d[0]; dims[1] = (int)t.d[1]; dims[2] = (int)t.d[2]; dims[3] = (int)t.d[3]; }
+        else { dims[0] = (int)t.d[0]; dims[1] = 0; dims[2] = (int)t.d[1]; dims[3] = (int)t.d[2]; }
+    });
+}
+
+extern "C" int ttipm_amen_get_core(ttipm_amen* h, int k, double* dst_host) {
+    TT_TRY(h, {
+        const Tensor& t = h->a.x[k];
+        to_host(h->a.c, t.p, (size_t)t.numel(), dst_host);
+    });
+}
+
+// stats[0..11]: [10] = seconds inside the Krylov kernel (only with profiling on), [11] = its algorithmic flops
+// stats[0..9] = sweeps, local solves, dense solves, Krylov solves, Krylov inner steps, Krylov matvecs, launches,
+//               host syncs, peak device bytes, trace rows; trace (may be NULL) receives 5 doubles per local solve
+extern "C" int ttipm_amen_stats(ttipm_amen* h, double* stats, double* trace, int max_trace_rows) {
+    TT_TRY(h, {
+        Amen& a = h->a;
+        double its = 0, mv = 0, lg_time = 0, lg_flops = 0;
+        for (size_t q = 0; q < a.lg_infos.size(); ++q) {
+            std::vector<double> v = read_vec(a.c, a.lg_infos[q]);
+            its += v[0];
+            mv += v[1];
+            const Amen::LgProf& pr = a.lg_prof[q];
+            const double kk = v[0] <= pr.restart ? v[0] * (v[0] + 1) / 2.0 : v[0] * (pr.restart + 1) / 2.0;
+            lg_flops += v[1] * pr.mv_flops + 4.0 * pr.nv * kk;
+#ifndef TTIPM_EMU
+            if (a.profile) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, pr.e0, pr.e1);
+                lg_time += ms * 1e-3;
+                cudaEventDestroy(pr.e0);
+                cudaEventDestroy(pr.e1);
+            }
+#endif
+        }
+        a.profile = false;
+        stats[10] = lg_time;
+        stats[11] = lg_flops;
+        stats[0] = a.sweeps; stats[1] = (double)a.local_solves; stats[2] = (double)a.dense_solves;
+        stats[3] = (double)a.lgmres_calls; stats[4] = its; stats[5] = mv; stats[6] = (double)a.c.launches;
+        stats[7] = (double)a.c.syncs; stats[8] = (double)a.c.bytes_peak; stats[9] = (double)(a.trace.size() / 5);
+        if (trace) {
+            const size_t rows = std::min<size_t>(a.trace.size() / 5, (size_t)max_trace_rows);
+            memcpy(trace, a.trace.data(), rows * 5 * sizeof(double));
+        }
+    });
+}

@@ -75,7 +75,7 @@ TT_GLOBAL void k_scale2d(const Scale2Params p) {
     const long total = (long)p.rows * p.cols, stride = (long)gridDim.x * blockDim.x;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
         const int i = (int)(e / p.cols), j = (int)(e % p.cols);
-        double sv = p.s[p.axis == 0 ? i : j];
+        const double sv = p.s ? p.s[p.axis == 0 ? i : j] : 1.0;
         double v = p.in[i * p.in_rs + j * p.in_cs];
         if (p.divide) v = sv != 0.0 ? v / sv : v;
         else v *= sv;

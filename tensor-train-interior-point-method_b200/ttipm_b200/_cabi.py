@@ -60,6 +60,18 @@ SIGNATURES = {
     "ttipm_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ttipm_scale2d": (C.c_int, [C.c_void_p, i64, i64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                 C.c_void_p]),
+    "ttipm_amen_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ttipm_amen_destroy": (None, [C.c_void_p]),
+    "ttipm_amen_set_block": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "ttipm_amen_add_alias": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ttipm_amen_set_rhs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "ttipm_amen_set_core": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ttipm_amen_run": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "ttipm_amen_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "ttipm_amen_core_shape": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(i32)]),
+    "ttipm_amen_get_core": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ttipm_amen_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "ttipm_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, i64, i64, i64, C.c_void_p, i64, i64,
                              i64, C.c_double, C.c_void_p, i64, i64, i64, C.c_int, C.c_void_p]),
 }

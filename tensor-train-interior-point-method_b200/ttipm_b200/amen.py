@@ -352,3 +352,139 @@ class DeviceBlockAmen:
         st = self.prepare(x0, kick_rank, amen)
         xd, final_res = self.run(st, term_tol, r_max, eps, nswp)
         return [self.rt.to_host(c) for c in xd], final_res
+
+
+class NativeBlockAmen:
+    """The same solve driven by the native C++ sweep driver (ttipm_amen_* in include/ttipm.h): Python uploads the
+    operands once, makes the reference's NumPy RNG draws, calls run() and fetches the result; every sweep, local
+    solve and rank decision in between happens inside libttipm_b200 without returning to the interpreter."""
+
+    def __init__(self, block_A, aliases, transposes, block_b, ineq, rt=None, stats=None):
+        import ctypes as C
+        self._C = C
+        self.rt = rt or get_runtime()
+        self.lib = self.rt.lib
+        self.block_size = max(k[0] for k in block_A.keys()) + 1
+        self.ineq = bool(ineq)
+        model = next(iter(block_b.values()))
+        self.d = len(model)
+        self.x_shape = tuple(model[0].shape[1:-1])
+        self.h = C.c_void_p(self.lib.ttipm_amen_create(self.d, self.block_size, int(self.ineq), self.rt.stream()))
+        self._keep = []
+        for (i, j), cores in block_A.items():
+            for k, c in enumerate(cores):
+                a = np.ascontiguousarray(c, dtype=np.float64)
+                self._chk(self.lib.ttipm_amen_set_block(self.h, i, j, k, a.ctypes.data, a.shape[0], a.shape[1], a.shape[3]))
+        for (i, j), (p, t) in aliases.items():
+            self._chk(self.lib.ttipm_amen_add_alias(self.h, i, j, p, t, 0))
+        for (i, j), (p, t) in transposes.items():
+            self._chk(self.lib.ttipm_amen_add_alias(self.h, i, j, p, t, 1))
+        for i, cores in block_b.items():
+            for k, c in enumerate(cores):
+                a = np.ascontiguousarray(c, dtype=np.float64)
+                self._chk(self.lib.ttipm_amen_set_rhs(self.h, i, k, a.ctypes.data, a.shape[0], a.shape[1], a.shape[2]))
+        self.stats = stats if stats is not None else {}
+        self.trace = []
+        self.sweeps = 0
+        self.ranks = []
+
+    def _chk(self, code):
+        if code != 0:
+            from .runtime import TTIPMError
+            raise TTIPMError(f"native AMEn driver failed ({code}): {self.lib.ttipm_last_error().decode()}")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.ttipm_amen_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _set_train(self, which, cores):
+        bs = self.block_size
+        for k, c in enumerate(cores):
+            a = np.ascontiguousarray(c, dtype=np.float64)
+            if a.ndim == 4:
+                self._chk(self.lib.ttipm_amen_set_core(self.h, which, k, a.ctypes.data, a.shape[0], a.shape[1], a.shape[2], a.shape[3]))
+            else:
+                self._chk(self.lib.ttipm_amen_set_core(self.h, which, k, a.ctypes.data, a.shape[0], 0, a.shape[1], a.shape[2]))
+
+    def prepare(self, x0=None, kick_rank=2, amen=True):
+        """Host set-up of tt_block_amen (reference src/tt_als.py:527-585): warm-start validation and the random
+        residual train, drawn in the reference's RNG order, then one upload."""
+        bs = self.block_size
+
+        def fresh():
+            from . import tt as T
+            from .runtime import use_runtime
+            with use_runtime(self.rt):
+                cores = T.tt_normalise([np.random.randn(1, *self.x_shape, 1) for _ in range(self.d - 1)])
+            return cores + [np.random.randn(1, bs, *self.x_shape, 1)]
+
+        direction = 1
+        if x0 is None:
+            xh = fresh()
+        else:
+            xh = x0
+            where = [i for i, c in enumerate(xh) if c.ndim == 4 and c.shape[1] == bs]
+            if len(where) != 1 or where[0] not in (0, len(xh) - 1):
+                xh = fresh()
+            elif where[0] == 0:
+                direction = -1
+        self._set_train(0, xh)
+        if amen:
+            kr = kick_rank
+            zh = [np.divide(1, np.prod(xh[0].shape[1:-1]) * kr ** 2) * np.random.randn(*xh[0].shape[:-1], kr)]
+            zh += [np.divide(1, np.prod(c.shape[1:-1]) * kr ** 2) * np.random.randn(kr, *c.shape[1:-1], kr)
+                   for c in xh[1:-1]]
+            zh += [np.divide(1, np.prod(xh[-1].shape[1:-1]) * kr ** 2) * np.random.randn(kr, *xh[-1].shape[1:])]
+            self._set_train(1, zh)
+        st = _State()
+        st.direction, st.amen, st.kick_rank = direction, amen, kick_rank
+        return st
+
+    def run(self, st, term_tol, r_max=100, eps=1e-12, nswp=22):
+        C = self._C
+        if self.stats.get("profile") is not None:
+            self.lib.ttipm_amen_set_profile(self.h, 1)
+        res = C.c_double(0.0)
+        sw = C.c_int(0)
+        self._chk(self.lib.ttipm_amen_run(self.h, term_tol, int(r_max), eps, int(nswp), int(st.kick_rank), int(st.amen),
+                                          int(st.direction), C.byref(res), C.byref(sw)))
+        self.sweeps = sw.value
+        return None, res.value
+
+    def fetch(self):
+        """Download the solution train (list of NumPy cores) and the run statistics."""
+        C = self._C
+        out = []
+        dims = (_cabi_i32() * 4)()
+        for k in range(self.d):
+            self._chk(self.lib.ttipm_amen_core_shape(self.h, k, dims))
+            shape = (dims[0], dims[1], dims[2], dims[3]) if dims[1] > 0 else (dims[0], dims[2], dims[3])
+            a = np.empty(shape, dtype=np.float64)
+            self._chk(self.lib.ttipm_amen_get_core(self.h, k, a.ctypes.data))
+            out.append(a)
+        self.ranks = [c.shape[0] for c in out[1:]]
+        stats = np.zeros(12)
+        self._chk(self.lib.ttipm_amen_stats(self.h, stats.ctypes.data, None, 0))
+        nrows = int(stats[9])
+        tr = np.zeros((max(nrows, 1), 5))
+        self._chk(self.lib.ttipm_amen_stats(self.h, stats.ctypes.data, tr.ctypes.data, nrows))
+        self.trace = [tuple(row) for row in tr[:nrows]]
+        self.native_stats = dict(zip(["sweeps", "local_solves", "dense_solves", "krylov_solves", "krylov_its",
+                                      "krylov_matvecs", "launches", "syncs", "peak_bytes", "trace_rows", "krylov_seconds",
+                                      "krylov_flops"], stats.tolist()))
+        self.stats.update(self.native_stats)
+        return out
+
+    def solve(self, term_tol, r_max=100, eps=1e-12, nswp=22, x0=None, kick_rank=2, amen=True):
+        st = self.prepare(x0, kick_rank, amen)
+        _, res = self.run(st, term_tol, r_max, eps, nswp)
+        return self.fetch(), res
+
+
+def _cabi_i32():
+    from . import _cabi
+    return _cabi.i32

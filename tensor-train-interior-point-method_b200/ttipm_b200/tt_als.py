@@ -11,7 +11,7 @@ import numpy as np
 
 from . import kernels as K
 from . import tt as T
-from .amen import DeviceBlockAmen
+from .amen import DeviceBlockAmen, NativeBlockAmen
 from .runtime import get_runtime
 from .tt import tt_mat_mat_mul, tt_mat_vec_mul  # noqa: F401  (re-exported, reference src/tt_als.py:1631,1765)
 
@@ -282,7 +282,8 @@ def tt_block_amen(block_A, block_b, term_tol, r_max=100, eps=1e-12, nswp=22, x0=
                   amen=False, verbose=False, _stats=None):
     """reference src/tt_als.py:525-670.  Returns (x_cores, final_local_residual)."""
     ineq = _solver_kind(local_solver, block_A)
-    dev = DeviceBlockAmen(block_A._data, block_A._aliases, block_A._transposes, block_b._data, ineq, stats=_stats)
+    driver = DeviceBlockAmen if (_stats or {}).get("driver") == "python" else NativeBlockAmen
+    dev = driver(block_A._data, block_A._aliases, block_A._transposes, block_b._data, ineq, stats=_stats)
     x, res = dev.solve(term_tol, r_max=r_max, eps=eps, nswp=nswp, x0=x0, kick_rank=kick_rank, amen=amen)
     if verbose:
         print(f"\\tSolution rank is {dev.ranks}\\n\\tResidual {res:.3e}\\n\\tNumber of sweeps {dev.sweeps}", flush=True)

@@ -28,10 +28,10 @@ def block_inner(bm, x, y=None):
     return sum(O.tt_inner_prod(O.tt_get_block(i, x), O.tt_get_block(i, y)) for i in range(nb))
 
 
-def run_block_amen(rt, path, use_oracle=True):
+def run_block_amen(rt, path, use_oracle=True, native=True):
     """tt_block_amen on one traced system with the device sweep (and optionally the oracle) from the
     same warm start and RNG state; returns a dict of comparisons."""
-    from ttipm_b200.amen import DeviceBlockAmen
+    from ttipm_b200.amen import DeviceBlockAmen, NativeBlockAmen
     g = G.load_amen(path)
     bm = O.BlockMatrix(g["A"], g["aliases"], g["transposes"])
     bv = O.BlockVector(g["b"])
@@ -45,8 +45,8 @@ def run_block_amen(rt, path, use_oracle=True):
         return x0
 
     kw = dict(r_max=g["rank_restriction"], eps=g["eps"], nswp=g["inner_m"], kick_rank=2, amen=True)
-    out = {"file": os.path.basename(path), "d": g["d"], "ineq": g["ineq"]}
-    dev = DeviceBlockAmen(g["A"], g["aliases"], g["transposes"], g["b"], g["ineq"], rt=rt)
+    out = {"file": os.path.basename(path), "d": g["d"], "ineq": g["ineq"], "native": native}
+    dev = (NativeBlockAmen if native else DeviceBlockAmen)(g["A"], g["aliases"], g["transposes"], g["b"], g["ineq"], rt=rt)
     x0 = prep()
     rt.sync()
     t0 = time.perf_counter()

@@ -11,9 +11,10 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("path", G.amen_files("amen_maxcut_5*") + G.amen_files("amen_maxcut_10*") +
                          G.amen_files("amen_corr_clust_8*") + G.amen_files("amen_max_stable_set_9*"),
                          ids=lambda p: p.split("amen_")[-1][:-4])
-def test_block_amen_matches_oracle(path):
+@pytest.mark.parametrize("native", [True, False], ids=["native", "python"])
+def test_block_amen_matches_oracle(path, native):
     rt = rt_util.cuda_runtime()
-    out = AC.run_block_amen(rt, path)
+    out = AC.run_block_amen(rt, path, native=native)
     print(out)
     assert out["sweeps_dev"] == out["sweeps_oracle"], out
     assert out["solves_dev"] == out["solves_oracle"], out
