@@ -329,6 +329,11 @@ static int prune_singular_vals(const std::vector<double>& s, double eps) {   // 
 // ---------------------------------------------------------------------------------------------------
 // dense Schur fallback: cuSOLVER / cuBLAS on row-major device matrices (reference src/tt_ipm.py:196-223, :298-334)
 // ---------------------------------------------------------------------------------------------------
+#ifndef TTIPM_EMU
+// library handles are expensive to create (tens of ms): one pair per process, re-bound to the caller's stream
+static cublasHandle_t g_blas = nullptr;
+static cusolverDnHandle_t g_sol = nullptr;
+#endif
 struct Dense {
     Ctx& c;
 #ifndef TTIPM_EMU
@@ -337,18 +342,15 @@ struct Dense {
 #endif
     explicit Dense(Ctx& ctx) : c(ctx) {
 #ifndef TTIPM_EMU
-        if (cublasCreate(&blas) != CUBLAS_STATUS_SUCCESS) throw DriverError(93, "cublasCreate failed");
-        if (cusolverDnCreate(&sol) != CUSOLVER_STATUS_SUCCESS) throw DriverError(93, "cusolverDnCreate failed");
+        if (!g_blas && cublasCreate(&g_blas) != CUBLAS_STATUS_SUCCESS) throw DriverError(93, "cublasCreate failed");
+        if (!g_sol && cusolverDnCreate(&g_sol) != CUSOLVER_STATUS_SUCCESS) throw DriverError(93, "cusolverDnCreate failed");
+        blas = g_blas;
+        sol = g_sol;
         cublasSetStream(blas, c.st);
         cusolverDnSetStream(sol, c.st);
 #endif
     }
-    ~Dense() {
-#ifndef TTIPM_EMU
-        if (sol) cusolverDnDestroy(sol);
-        if (blas) cublasDestroy(blas);
-#endif
-    }
+    ~Dense() {}
     // C (M x N) = alpha * op(A) op(B) + beta * C, all row-major contiguous
     void gemm(bool ta, bool tb, long M, long N, long K, double alpha, const double* A, const double* B, double beta, double* C) {
 #ifdef TTIPM_EMU
@@ -527,7 +529,8 @@ struct Amen {
         int restart;
     };
     std::vector<LgProf> lg_prof;               // one record per Krylov solve (same order as lg_infos)
-    bool profile = false;
+    bool profile = false, stats_done = false;
+    double lg_time = 0.0, lg_flops = 0.0;
     std::string error;
 
     Tensor ones(std::initializer_list<long> dims) {
@@ -1071,6 +1074,21 @@ struct ttipm_amen {
     }
 
 extern "C" ttipm_amen* ttipm_amen_create(int d, int block_size, int ineq, void* stream) {
+#ifndef TTIPM_EMU
+    {   // keep freed blocks in the stream-ordered pool across synchronisations (the default trims it to zero)
+        static bool pool_ready = false;
+        if (!pool_ready) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_ready = true;
+        }
+    }
+#endif
     ttipm_amen* h = new ttipm_amen();
     h->a.c.st = (tt_stream_t)stream;
     h->a.d = d;
@@ -1167,6 +1185,7 @@ extern "C" int ttipm_amen_run(ttipm_amen* h, double term_tol, int r_max, double 
             }
         }
         a.trace.clear();
+        a.stats_done = false;
         const double res = a.run(term_tol, r_max, eps, nswp, direction);
         if (final_res) *final_res = res;
         if (sweeps) *sweeps = a.sweeps;
@@ -1200,27 +1219,30 @@ extern "C" int ttipm_amen_get_core(ttipm_amen* h, int k, double* dst_host) {
 extern "C" int ttipm_amen_stats(ttipm_amen* h, double* stats, double* trace, int max_trace_rows) {
     TT_TRY(h, {
         Amen& a = h->a;
-        double its = 0, mv = 0, lg_time = 0, lg_flops = 0;
-        for (size_t q = 0; q < a.lg_infos.size(); ++q) {
-            std::vector<double> v = read_vec(a.c, a.lg_infos[q]);
-            its += v[0];
-            mv += v[1];
-            const Amen::LgProf& pr = a.lg_prof[q];
-            const double kk = v[0] <= pr.restart ? v[0] * (v[0] + 1) / 2.0 : v[0] * (pr.restart + 1) / 2.0;
-            lg_flops += v[1] * pr.mv_flops + 4.0 * pr.nv * kk;
+        if (!a.stats_done) {
+            for (size_t q = 0; q < a.lg_infos.size(); ++q) {
+                std::vector<double> v = read_vec(a.c, a.lg_infos[q]);
+                a.lgmres_its += (long)v[0];
+                a.lgmres_matvecs += (long)v[1];
+                const Amen::LgProf& pr = a.lg_prof[q];
+                const double kk = v[0] <= pr.restart ? v[0] * (v[0] + 1) / 2.0 : v[0] * (pr.restart + 1) / 2.0;
+                a.lg_flops += v[1] * pr.mv_flops + 4.0 * pr.nv * kk;
 #ifndef TTIPM_EMU
-            if (a.profile) {
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, pr.e0, pr.e1);
-                lg_time += ms * 1e-3;
-                cudaEventDestroy(pr.e0);
-                cudaEventDestroy(pr.e1);
-            }
+                if (a.profile) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, pr.e0, pr.e1);
+                    a.lg_time += ms * 1e-3;
+                    cudaEventDestroy(pr.e0);
+                    cudaEventDestroy(pr.e1);
+                }
 #endif
+            }
+            a.profile = false;
+            a.stats_done = true;
         }
-        a.profile = false;
-        stats[10] = lg_time;
-        stats[11] = lg_flops;
+        const double its = (double)a.lgmres_its, mv = (double)a.lgmres_matvecs;
+        stats[10] = a.lg_time;
+        stats[11] = a.lg_flops;
         stats[0] = a.sweeps; stats[1] = (double)a.local_solves; stats[2] = (double)a.dense_solves;
         stats[3] = (double)a.lgmres_calls; stats[4] = its; stats[5] = mv; stats[6] = (double)a.c.launches;
         stats[7] = (double)a.c.syncs; stats[8] = (double)a.c.bytes_peak; stats[9] = (double)(a.trace.size() / 5);
