@@ -295,12 +295,8 @@ def main():
         e2e_times.append(t)
     clocks.stop_flag = True
     clocks.join(timeout=2)
-    if world > 1:
-        tt_ = torch.tensor([total, float(np.mean(e2e_times))], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
-        total, e2e_mean = float(tt_[0]), float(tt_[1])
-    else:
-        e2e_mean = float(np.mean(e2e_times))
+    from ttipm_b200 import replicas
+    total, e2e_mean = replicas.max_over_ranks([total, float(np.mean(e2e_times))], device=dev)
 
     # ---- roofline of the dominant kernel (persistent LGMRES): one instrumented pass ---------------------
     prof = []

@@ -1,0 +1,95 @@
+"""CPU tier: the whole hot path (native C++ sweep driver + the real kernel sources under -DTTIPM_EMU) on the
+smallest traced KKT systems vs the oracle, and the host mirror's containers / dispatch logic."""
+import numpy as np
+import pytest
+
+import golden_io as G
+import rt_util
+import amen_cases as AC
+import tt_oracle as O
+
+
+@pytest.fixture(scope="module")
+def rt():
+    return rt_util.emu_runtime()
+
+
+@pytest.mark.parametrize("native", [True, False], ids=["native", "python"])
+def test_block_amen_maxcut5(rt, native):
+    out = AC.run_block_amen(rt, G.amen_files("amen_maxcut_5_r1_s319_1*")[0], native=native)
+    assert out["sweeps_dev"] == out["sweeps_oracle"] and out["solves_dev"] == out["solves_oracle"], out
+    assert out["ranks_dev"] == out["ranks_oracle"], out
+    assert out["sol_rel_diff"] < 1e-7 and out["trace_absdiff"] < 1e-9, out   # norm via inner products: sqrt(eps) floor
+
+
+def test_restarted_block_amen_through_mirror(rt):
+    """ttipm_b200.tt_als.tt_restarted_block_amen with the reference's call convention (local_solver callback
+    dispatched by name, NumPy in / NumPy out, warm-start retraction) vs the reference's own output."""
+    from ttipm_b200 import tt_als, use_runtime
+    g = G.load_amen(G.amen_files("amen_maxcut_5_r1_s319_6*")[0])
+    A = tt_als.TTBlockMatrix()
+    for key, cores in g["A"].items():
+        A[key] = [c.copy() for c in cores]
+    for k1, k2 in g["aliases"].items():
+        A.add_alias(k1, k2)
+    for k1, k2 in g["transposes"].items():
+        A.add_alias(k1, k2, is_transpose=True)
+    b = tt_als.TTBlockVector()
+    for i, cores in g["b"].items():
+        b[i] = [c.copy() for c in cores]
+
+    def _ipm_local_solver(*a, **k):     # never called: the device sweep dispatches on the name
+        raise AssertionError("host callback must not run")
+
+    np.random.set_state(g["rng_state"])
+    with use_runtime(rt):
+        x, res = tt_als.tt_restarted_block_amen(A, b, g["rank_restriction"], g["op_tol"], termination_tol=g["termination_tol"],
+                                                eps=g["eps"], num_restarts=g["num_restarts"], inner_m=g["inner_m"],
+                                                x0=[c.copy() for c in g["x0"]], local_solver=_ipm_local_solver)
+    assert O.tt_ranks(x) == O.tt_ranks(g["out_x"])
+    for i in range(3):
+        assert AC.rel(AC.dense_block(x, i), AC.dense_block(g["out_x"], i)) < 1e-6
+    assert res <= max(10 * g["out_res"], 1e-10)
+
+
+def test_container_semantics():
+    from ttipm_b200 import tt_als
+    A = tt_als.TTBlockMatrix()
+    assert A[0, 1] == [] and (0, 1) in A.keys()              # __getitem__ has setdefault semantics (src/tt_als.py:100-102)
+    A[2, 1] = [np.zeros((1, 4, 4, 1))]
+    A[3, 3] = [np.zeros((1, 4, 4, 1))]
+    A.add_alias((0, 1), (1, 0), is_transpose=True)
+    A.add_alias((1, 2), (1, 3))
+    assert A.tkeys() == {(0, 1), (2, 1), (3, 3), (1, 0)}
+    assert A.akeys() == {(0, 1), (2, 1), (3, 3), (1, 3)}
+    sub = A.get_submatrix(2, 2)
+    assert (3, 3) not in sub.keys() and sub._aliases == {} and sub._transposes == {(0, 1): (1, 0)}
+    with pytest.raises(KeyError):
+        A["x"]
+    b = tt_als.TTBlockVector()
+    with pytest.raises(ValueError):
+        b[0] = np.zeros(3)
+    b[1] = [np.ones((1, 4, 1))]
+    assert b.get_row(0) is None and list(b.keys()) == [1]
+    def _ipm_local_solver_ineq():
+        pass
+
+    def _ipm_local_solver():
+        pass
+    assert tt_als._solver_kind(_ipm_local_solver_ineq, A) is True
+    assert tt_als._solver_kind(_ipm_local_solver, A) is False
+    with pytest.raises(NotImplementedError):
+        tt_als._solver_kind(None, A)
+
+
+def test_restarted_raises_on_tiny_rhs(rt):
+    from ttipm_b200 import tt_als, use_runtime
+    A = tt_als.TTBlockMatrix()
+    A[0, 0] = [np.eye(4).reshape(1, 4, 4, 1)] * 2
+    b = tt_als.TTBlockVector()
+    b[0] = [1e-9 * np.ones((1, 4, 1))] * 2
+
+    def _ipm_local_solver():
+        pass
+    with use_runtime(rt), pytest.raises(RuntimeError):
+        tt_als.tt_restarted_block_amen(A, b, 10, 1e-4, local_solver=_ipm_local_solver)
