@@ -120,18 +120,26 @@ int ttipm_local_lgmres(int ineq, const ttipm_term* K00, const ttipm_term* K01, c
                        int restart, int augment, int max_it, double rtol, int apply_only, int grid_hint,
                        double* info, void* stream);
 
-/* ---- dense factorisations of core unfoldings (one CTA per matrix, batched) ---------------------- */
+/* ---- dense factorisations of core unfoldings ------------------------------------------------- */
+/* One kernel serves every shape (csrc/linalg.cu): a single matrix with min(M, N) >= the threshold below runs as one
+ * cooperative multi-CTA launch (panel Householder QR + QR-preconditioned block one-sided Jacobi); smaller or batched
+ * matrices use one CTA per matrix.  The setter returns the previous threshold (default 17); min_dim <= 0 only queries. */
+int ttipm_linalg_coop_min_dim(int min_dim);
+
 /* Householder QR, A (M x N, strided) = Q (M x K) R (K x N), K = min(M, N); Q, R contiguous row-major.
  * Replaces scipy.linalg.qr(mode="economic") at reference cy_src/tt_ops_cy.pyx:147, src/tt_als.py:358, :482.
- * workspace: ttipm_qr_workspace() doubles (only touched when the matrix does not fit in shared memory). */
+ * workspace: ttipm_qr_workspace() doubles (required). */
 int64_t ttipm_qr_workspace(int M, int N, int nbatch);
 int ttipm_qr(const double* A, int64_t a_rs, int64_t a_cs, int64_t a_bs, int M, int N, double* Q, double* R,
              double* workspace, int nbatch, void* stream);
 
-/* "Left" SVD by one-sided Jacobi: A (M x N, strided) -> U (M x K), S (K, descending), Wt = S * V^T (K x N).
- * Replaces scipy.linalg.svd at reference cy_src/tt_ops_cy.pyx:205,:291,:357,:404,:418 and
+/* "Left" SVD by QR-preconditioned one-sided Jacobi: A (M x N, strided) -> U (M x K), S (K, descending),
+ * Wt = S * V^T (K x N).  Replaces scipy.linalg.svd at reference cy_src/tt_ops_cy.pyx:205,:291,:357,:404,:418 and
  * src/tt_als.py:270,:331,:457 -- every call site there only consumes U, s and s*Vt.
- * info (device int32 per batch entry, may be NULL) receives the number of Jacobi sweeps. */
+ * workspace: ttipm_svd_workspace() doubles (required).
+ * info (device int32[16] per batch entry, may be NULL): [0] = Jacobi sweeps, [1..3] = ns spent in QR / Q^T set-up /
+ * Jacobi, [4] = CTAs per matrix, [5] = Jacobi block rows, [6..9] = Jacobi breakdown on CTA 0 (row loads, rotations,
+ * row stores, grid barriers; ns), [10] = total ns. */
 int64_t ttipm_svd_workspace(int M, int N, int nbatch);
 int ttipm_svd_left(const double* A, int64_t a_rs, int64_t a_cs, int64_t a_bs, int M, int N, double* U, double* S,
                    double* Wt, double* workspace, int32_t* info, int nbatch, void* stream);

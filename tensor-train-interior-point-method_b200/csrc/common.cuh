@@ -222,7 +222,16 @@ int launch_kernel(const char* name, void (*kern)(P), dim3 grid, dim3 block, size
     return 0;
 #else
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // opt in to the device maximum (never to `smem` itself: a later, larger launch of the same kernel would find the
+        // attribute lowered and its occupancy query would report zero resident CTAs)
+        static int optin_max = 0;
+        if (!optin_max) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&optin_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        }
+        cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             optin_max > (int)smem ? optin_max : (int)smem);
         if (e != cudaSuccess) {
             set_error("%s: cannot opt in to %zu B of shared memory: %s", name, smem, cudaGetErrorString(e));
             return 2;

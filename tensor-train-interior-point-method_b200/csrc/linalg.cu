@@ -1,296 +1,620 @@
-// Small dense factorisations of core unfoldings, one CTA per matrix (batched over blockIdx.x):
-//   * Householder QR  (replaces scipy.linalg.qr / LAPACK geqrf+orgqr at reference
-//     cy_src/tt_ops_cy.pyx:147, src/tt_als.py:358, :482)
-//   * "left" SVD by one-sided Jacobi on the rows with accumulated rotations
-//     (replaces scipy.linalg.svd / LAPACK gesvd, gesdd at cy_src/tt_ops_cy.pyx:205, :404, :418 and
-//     src/tt_als.py:270, :331, :457).  Every caller on the hot path only needs U, s and S*V^T, so
-//     the kernel returns exactly those: U is a product of plane rotations (orthonormal even for zero
-//     singular values) and W = S V^T are the rotated rows themselves (no division by s anywhere).
-// Working arrays live in shared memory when they fit, otherwise in a caller-provided workspace.
+// Dense factorisations of core unfoldings: Householder QR and the "left" SVD (U, s, S*V^T).
+//
+//   * QR replaces scipy.linalg.qr / LAPACK geqrf+orgqr at reference cy_src/tt_ops_cy.pyx:147,
+//     src/tt_als.py:358, :482.
+//   * The SVD replaces scipy.linalg.svd / LAPACK gesvd, gesdd at cy_src/tt_ops_cy.pyx:205, :404, :418 and
+//     src/tt_als.py:270, :331, :457.  Every caller on the hot path only needs U, s and S*V^T, so the kernel
+//     returns exactly those: U is a product of Householder reflectors and plane rotations (orthonormal even
+//     for zero singular values) and W = S V^T is never divided by s.
+//
+// ONE kernel (k_linalg) serves every shape.  A single large matrix runs as a persistent cooperative launch
+// over several CTAs (grid.x > 1, grid barriers between phases); small or batched matrices use one CTA per
+// matrix (grid.y = batch) and the same code with block barriers only.  Phases:
+//   QR      panel Householder: the panel of TT_QR_PB columns is factored in shared memory (redundantly by
+//           every CTA, so no broadcast is needed), trailing columns are owned by warps across the grid and
+//           held in registers while the panel's reflectors are applied; one grid barrier per panel.
+//   Q       reflectors are staged panel by panel in shared memory and applied to register-resident vectors
+//           (unit vectors -> rows of Q^T, or [g; 0] -> rows of G Q^T), one vector per warp, no grid barrier.
+//   Jacobi  QR-preconditioned BLOCK one-sided Jacobi on the rows of the triangular factor R (K x K):
+//           tall A = Q R        -> rotate rows of R, accumulator starts from Q^T   (rows end as U^T)
+//           wide A^T = Q1 R1, R1^T = Q2 R2 -> rotate rows of R2, accumulator starts from Q2^T,
+//                                  W = (rotated rows) Q1^T at the end
+//           (rows of an unpreconditioned wide matrix need 40-50 sweeps, rows of R need ~10).
+//           A CTA owns a pair of row blocks per round, keeps their rows of R and of the accumulator in shared
+//           memory and orthogonalises every cross pair (intra-block pairs once per sweep); block pairs follow
+//           a round-robin tournament with one grid barrier per round (K / nb rounds per sweep instead of K).
 #include "api_util.h"
 
 namespace ttipm {
 
-// ---- Householder QR on a column-major working copy W (M x N, leading dim M) ------------------------
-// On exit W holds R in its upper triangle and the reflector tails below the diagonal, tau[K].
-TT_DEV void qr_factor(double* W, double* tau, int M, int N, double* scr) {
-    const int K = imin(M, N);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int j = 0; j < K; ++j) {
-        double* col = W + (long)j * M;
-        double s = 0.0;
-        for (int i = j + 1 + threadIdx.x; i < M; i += blockDim.x) s += col[i] * col[i];
-        s = block_sum(s, scr);
-        const double alpha = col[j];
-        double tj = 0.0, scale = 0.0, beta = alpha;
-        if (s != 0.0) {
-            beta = -copysign(sqrt(alpha * alpha + s), alpha);
-            tj = (beta - alpha) / beta;
-            scale = 1.0 / (alpha - beta);
-        }
-        __syncthreads();
-        for (int i = j + 1 + threadIdx.x; i < M; i += blockDim.x) col[i] *= scale;
-        if (threadIdx.x == 0) {
-            tau[j] = tj;
-            col[j] = beta;
-        }
-        __syncthreads();
-        if (tj != 0.0) {
-            for (int c = j + 1 + wid; c < N; c += nw) {
-                double* cc = W + (long)c * M;
-                double d = lane == 0 ? cc[j] : 0.0;
-                for (int i = j + 1 + lane; i < M; i += 32) d += col[i] * cc[i];
-                d = warp_sum(d) * tj;
-                if (lane == 0) cc[j] -= d;
-                for (int i = j + 1 + lane; i < M; i += 32) cc[i] -= d * col[i];
-            }
-        }
-        __syncthreads();
-    }
-}
+#define TT_QR_PB 8
+#define TT_LIN_REG 16          // register-resident vector length = 32 * TT_LIN_REG
 
-// Q (M x K, element (i, c) at Q[i * q_rs + c * q_cs]) = H_0 ... H_{K-1} applied to the first K unit vectors
-TT_DEV void qr_form_q(const double* W, const double* tau, int M, int N, double* Q, long q_rs, long q_cs) {
-    const int K = imin(M, N);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
-        const int row = i / K, c = i % K;
-        Q[row * q_rs + c * q_cs] = row == c ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    for (int j = K - 1; j >= 0; --j) {
-        const double tj = tau[j];
-        const double* v = W + (long)j * M;
-        if (tj != 0.0) {
-            for (int c = j + wid; c < K; c += nw) {
-                double d = lane == 0 ? Q[j * q_rs + c * q_cs] : 0.0;
-                for (int i = j + 1 + lane; i < M; i += 32) d += v[i] * Q[i * q_rs + c * q_cs];
-                d = warp_sum(d) * tj;
-                if (lane == 0) Q[j * q_rs + c * q_cs] -= d;
-                for (int i = j + 1 + lane; i < M; i += 32) Q[i * q_rs + c * q_cs] -= d * v[i];
-            }
-        }
-        __syncthreads();
-    }
-}
-
-struct QrParams {
+struct LinParams {
     const double* A;
     long a_rs, a_cs, a_bs;
     int M, N;
-    double* Q;   // batch x M x K row-major
-    double* R;   // batch x K x N row-major
-    double* ws;  // batch x (M*N + K) when the working copy does not fit in shared memory
-    int use_smem;
+    int mode;            // 0 = SVD: U (M x K), S (K), Wt (K x N)     1 = QR: U = Q (M x K), Wt = R (K x N)
+    double* U;
+    double* S;
+    double* Wt;
+    int* info;           // 16 ints per batch entry or NULL
+    double* ws;          // [nbatch x 40 doubles: sweep flags + barrier][nbatch x ws_per]
+    long ws_per;
+    long oW1, oTau1, oW2, oTau2, oG, oJt, oSv;      // offsets inside one batch workspace
+    int M1, N1;          // first QR: M x N (tall, square, QR mode) or N x M (wide SVD, factors A^T)
+    int Mj;              // accumulator row length
+    int nb;              // Jacobi block rows
+    int ldp;             // panel leading dimension in shared memory
+    int oOrd, oSvS, oTaus, oP;   // shared-memory offsets (doubles)
+    int nbatch;
 };
 
-TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_qr(const QrParams p) {
-    TT_SMEM_DECL(smem_raw);
-    double* smem = (double*)smem_raw;
-    const int M = p.M, N = p.N, K = imin(M, N);
-    double* scr = smem;
-    double* W = p.use_smem ? smem + 40 : p.ws + (long)blockIdx.x * ((long)M * N + K);
-    double* tau = W + (long)M * N;
-    const double* A = p.A + blockIdx.x * p.a_bs;
-    for (int i = threadIdx.x; i < M * N; i += blockDim.x) {
-        const int row = i / N, c = i % N;
-        W[row + (long)c * M] = A[row * p.a_rs + c * p.a_cs];
+struct LinCtx {
+    const LinParams& p;
+    double* smem;
+    unsigned* barrier;
+    unsigned epoch;
+    int lane, wid, nw, gw, GW;
+    TT_DEVM LinCtx(const LinParams& pp, double* s, unsigned* bar) : p(pp), smem(s), barrier(bar), epoch(0) {
+        lane = threadIdx.x & 31;
+        wid = threadIdx.x >> 5;
+        nw = blockDim.x >> 5;
+        gw = blockIdx.x * nw + wid;
+        GW = gridDim.x * nw;
     }
-    __syncthreads();
-    qr_factor(W, tau, M, N, scr);
-    double* R = p.R + (long)blockIdx.x * K * N;
-    for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
-        const int row = i / N, c = i % N;
-        R[i] = row <= c ? W[row + (long)c * M] : 0.0;
+    TT_DEVM void sync() { grid_sync(barrier, epoch); }
+};
+
+#ifndef TTIPM_EMU
+TT_DEV long long lin_now() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+TT_DEV double lin_rsqrt(double x) { return rsqrt(x); }
+#else
+TT_DEV long long lin_now() { return 0; }
+TT_DEV double lin_rsqrt(double x) { return 1.0 / sqrt(x); }
+#endif
+
+// x <- (I - tj v v^T) x for a vector held in registers with the fixed mapping element i <-> (lane, q = i / 32);
+// v[j] = 1 implicit, v[i] given for j < i < len (v may point before its first valid element), zero above j
+TT_DEV void lin_reflect_reg(double (&reg)[TT_LIN_REG], const double* v, int j, int len, double tj, int lane) {
+    double vv[TT_LIN_REG];
+    double d = 0.0;
+#pragma unroll
+    for (int q = 0; q < TT_LIN_REG; ++q) {
+        const int i = lane + 32 * q;
+        vv[q] = (i > j && i < len) ? v[i] : (i == j ? 1.0 : 0.0);
+        d += vv[q] * reg[q];
     }
-    qr_form_q(W, tau, M, N, p.Q + (long)blockIdx.x * M * K, K, 1);
+    d = warp_sum(d) * tj;
+#pragma unroll
+    for (int q = 0; q < TT_LIN_REG; ++q) reg[q] -= d * vv[q];
+}
+// same for a vector in memory (len > 32 * TT_LIN_REG); element i at x[i * xs]; a thread only re-reads its own writes
+TT_DEV void lin_reflect_mem(double* x, long xs, const double* v, int j, int len, double tj, int lane) {
+    double d = 0.0;
+    for (int i = lane; i < len; i += 32) {
+        if (i > j) d += v[i] * ld_cg(x + (long)i * xs);
+        else if (i == j) d += ld_cg(x + (long)i * xs);
+    }
+    d = warp_sum(d) * tj;
+    for (int i = lane; i < len; i += 32) {
+        if (i > j) x[(long)i * xs] = ld_cg(x + (long)i * xs) - d * v[i];
+        else if (i == j) x[(long)i * xs] = ld_cg(x + (long)i * xs) - d;
+    }
 }
 
-// ---- one-sided Jacobi on the rows of G (K x N row-major), Jt accumulates the rotations -------------
-// On exit the rows of G are mutually orthogonal: G[i,:] = s_i v_i^T and column i of J = Jt[i,:] is u_i.
-TT_DEV int jacobi_rows(double* G, double* Jt, int K, int N, int* flag) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int Ke = K + (K & 1);
-    const double tol = 2.220446049250313e-16 * sqrt((double)N);
-    int sweeps = 0;
-    if (K < 2) return 0;
-    for (; sweeps < 60; ++sweeps) {
-        if (threadIdx.x == 0) *flag = 0;
+// stage reflectors [j0, j0 + pw) of W (column-major Mq x *, rows j0.. only) and their tau into shared memory
+TT_DEV void lin_load_panel(const double* W, const double* tau, int Mq, int j0, int pw, bool with_tau, double* P,
+                           double* taus, int ldp) {
+    const int rows = Mq - j0;
+    for (int i = threadIdx.x; i < pw * rows; i += blockDim.x) {
+        const int j = i / rows, q = i % rows;
+        P[j * ldp + q] = ld_cg(W + (long)(j0 + j) * Mq + j0 + q);
+    }
+    if (with_tau && (int)threadIdx.x < pw) taus[threadIdx.x] = ld_cg(tau + j0 + threadIdx.x);
+}
+
+// W (Mq x Nq column-major, global) -> R in the upper triangle, reflector tails below, tau[min(Mq, Nq)].
+// Ends with a grid barrier.
+TT_DEV void lin_qr_factor(LinCtx& c, double* W, double* tau, int Mq, int Nq) {
+    const int K = imin(Mq, Nq), ldp = c.p.ldp, lane = c.lane, wid = c.wid, nw = c.nw;
+    double* taus = c.smem + c.p.oTaus;
+    double* P = c.smem + c.p.oP;
+    for (int p0 = 0; p0 < K; p0 += TT_QR_PB) {
+        const int pw = imin(TT_QR_PB, K - p0), rows = Mq - p0;
         __syncthreads();
-        for (int t = 0; t < Ke - 1; ++t) {
-            for (int pi = wid; pi < Ke / 2; pi += nw) {
-                int a, b;
-                if (pi == 0) {
-                    a = Ke - 1;
-                    b = t;
-                } else {
-                    a = (t + pi) % (Ke - 1);
-                    b = (t - pi + Ke - 1) % (Ke - 1);
+        lin_load_panel(W, nullptr, Mq, p0, pw, false, P, taus, ldp);
+        __syncthreads();
+        for (int j = 0; j < pw; ++j) {
+            double* col = P + j * ldp;
+            if (wid == 0) {
+                double s = 0.0;
+                for (int i = j + 1 + lane; i < rows; i += 32) s += col[i] * col[i];
+                s = warp_sum(s);
+                const double alpha = col[j];
+                double tj = 0.0, scale = 0.0, beta = alpha;
+                if (s != 0.0) {
+                    beta = -copysign(sqrt(alpha * alpha + s), alpha);
+                    tj = (beta - alpha) / beta;
+                    scale = 1.0 / (alpha - beta);
                 }
-                if (a >= K || b >= K) continue;
-                if (a > b) { const int q = a; a = b; b = q; }
-                double* ga = G + (long)a * N;
-                double* gb = G + (long)b * N;
-                double saa = 0.0, sbb = 0.0, sab = 0.0;
-                for (int i = lane; i < N; i += 32) {
-                    const double x = ga[i], y = gb[i];
-                    saa += x * x;
-                    sbb += y * y;
-                    sab += x * y;
+                __syncwarp();                                  // every lane has read col[j] before lane 0 overwrites it
+                for (int i = j + 1 + lane; i < rows; i += 32) col[i] *= scale;
+                if (lane == 0) {
+                    taus[j] = tj;
+                    col[j] = beta;
                 }
-                saa = warp_sum(saa);
-                sbb = warp_sum(sbb);
-                sab = warp_sum(sab);
-                if (fabs(sab) > tol * sqrt(saa * sbb) && sab != 0.0) {
-                    const double zeta = (sbb - saa) / (2.0 * sab);
-                    const double tg = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double cs = 1.0 / sqrt(1.0 + tg * tg), sn = cs * tg;
-                    for (int i = lane; i < N; i += 32) {
-                        const double x = ga[i], y = gb[i];
-                        ga[i] = cs * x - sn * y;
-                        gb[i] = sn * x + cs * y;
-                    }
-                    double* ja = Jt + (long)a * K;
-                    double* jb = Jt + (long)b * K;
-                    for (int i = lane; i < K; i += 32) {
-                        const double x = ja[i], y = jb[i];
-                        ja[i] = cs * x - sn * y;
-                        jb[i] = sn * x + cs * y;
-                    }
-                    if (lane == 0) *flag = 1;
+            }
+            __syncthreads();
+            const double tj = taus[j];
+            if (tj != 0.0) {
+                for (int cc = j + 1 + wid; cc < pw; cc += nw) {
+                    double* x = P + cc * ldp;
+                    double d = lane == 0 ? x[j] : 0.0;
+                    for (int i = j + 1 + lane; i < rows; i += 32) d += col[i] * x[i];
+                    d = warp_sum(d) * tj;
+                    if (lane == 0) x[j] -= d;
+                    for (int i = j + 1 + lane; i < rows; i += 32) x[i] -= d * col[i];
                 }
             }
             __syncthreads();
         }
-        const int any = *flag;
-        __syncthreads();
-        if (!any) break;
+        if (blockIdx.x == 0) {
+            for (int i = threadIdx.x; i < pw * rows; i += blockDim.x) {
+                const int j = i / rows, q = i % rows;
+                W[(long)(p0 + j) * Mq + p0 + q] = P[j * ldp + q];
+            }
+            if ((int)threadIdx.x < pw) tau[p0 + threadIdx.x] = taus[threadIdx.x];
+        }
+        for (int cc = p0 + pw + c.gw; cc < Nq; cc += c.GW) {
+            double* x = W + (long)cc * Mq + p0;
+            if (rows <= 32 * TT_LIN_REG) {
+                double reg[TT_LIN_REG];
+#pragma unroll
+                for (int q = 0; q < TT_LIN_REG; ++q) {
+                    const int i = lane + 32 * q;
+                    reg[q] = i < rows ? ld_cg(x + i) : 0.0;
+                }
+                for (int j = 0; j < pw; ++j)
+                    if (taus[j] != 0.0) lin_reflect_reg(reg, P + j * ldp, j, rows, taus[j], lane);
+#pragma unroll
+                for (int q = 0; q < TT_LIN_REG; ++q) {
+                    const int i = lane + 32 * q;
+                    if (i < rows) x[i] = reg[q];
+                }
+            } else {
+                for (int j = 0; j < pw; ++j)
+                    if (taus[j] != 0.0) lin_reflect_mem(x, 1, P + j * ldp, j, rows, taus[j], lane);
+            }
+        }
+        c.sync();
+    }
+}
+
+// One vector per warp task t < ntask:  x_t <- H_0 H_1 ... H_{Kq-1} x_t   (= Q x_t, reflectors of a factored W).
+//   init 0: x_t = e_t (only H_j with j <= t act)            -> column t of Q
+//   init 1: x_t = [src[ord[t], 0:Kq] ; 0]                    -> Q [g; 0]
+// Result element i of task t goes to dst[t * row_stride + i * elem_stride].  W, tau, src must be globally visible.
+TT_DEV void lin_apply_q(LinCtx& c, const double* W, const double* tau, int Mq, int Kq, int ntask, int init,
+                        const double* src, const int* ord, double* dst, long row_stride, long elem_stride) {
+    const int ldp = c.p.ldp, lane = c.lane;
+    double* taus = c.smem + c.p.oTaus;
+    double* P = c.smem + c.p.oP;
+    const bool in_regs = Mq <= 32 * TT_LIN_REG;
+    for (int base = 0; base < ntask; base += c.GW) {
+        const int first = base + blockIdx.x * c.nw;
+        if (first >= ntask) break;                              // uniform over the CTA
+        const int t = first + c.wid;
+        const bool active = t < ntask;
+        const int tmax = imin(ntask - 1, first + c.nw - 1);
+        const int jtop = init == 0 ? imin(tmax, Kq - 1) : Kq - 1;
+        double reg[TT_LIN_REG];
+        double* x = dst + (long)t * row_stride;
+        if (active) {
+            if (in_regs) {
+#pragma unroll
+                for (int q = 0; q < TT_LIN_REG; ++q) {
+                    const int i = lane + 32 * q;
+                    if (init == 0) reg[q] = i == t ? 1.0 : 0.0;
+                    else reg[q] = i < Kq ? ld_cg(src + (long)ord[t] * Kq + i) : 0.0;
+                }
+            } else {
+                for (int i = lane; i < Mq; i += 32) {
+                    double v;
+                    if (init == 0) v = i == t ? 1.0 : 0.0;
+                    else v = i < Kq ? ld_cg(src + (long)ord[t] * Kq + i) : 0.0;
+                    x[(long)i * elem_stride] = v;
+                }
+            }
+        }
+        for (int j0 = (jtop / TT_QR_PB) * TT_QR_PB; j0 >= 0; j0 -= TT_QR_PB) {
+            const int pw = imin(TT_QR_PB, Kq - j0);
+            __syncthreads();
+            lin_load_panel(W, tau, Mq, j0, pw, true, P, taus, ldp);
+            __syncthreads();
+            if (!active) continue;
+            for (int jj = pw - 1; jj >= 0; --jj) {
+                const int j = j0 + jj;
+                if (init == 0 && j > t) continue;
+                const double tj = taus[jj];
+                if (tj == 0.0) continue;
+                const double* v = P + jj * ldp - j0;            // v[i] valid for j < i < Mq
+                if (in_regs) lin_reflect_reg(reg, v, j, Mq, tj, lane);
+                else lin_reflect_mem(x, elem_stride, v, j, Mq, tj, lane);
+            }
+        }
+        if (active && in_regs) {
+#pragma unroll
+            for (int q = 0; q < TT_LIN_REG; ++q) {
+                const int i = lane + 32 * q;
+                if (i < Mq) x[(long)i * elem_stride] = reg[q];
+            }
+        }
+    }
+}
+
+// orthogonalise two rows held in shared memory: [row of R (K) | accumulator row (Mj)], total length Ls
+TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, int lane) {
+    double saa = 0.0, sbb = 0.0, sab = 0.0;
+    for (int i = lane; i < K; i += 32) {
+        const double x = ra[i], y = rb[i];
+        saa += x * x;
+        sbb += y * y;
+        sab += x * y;
+    }
+    saa = warp_sum(saa);
+    sbb = warp_sum(sbb);
+    sab = warp_sum(sab);
+    if (!(sab * sab > tol2 * saa * sbb)) return false;
+    // tan of the rotation angle: zeta = (sbb - saa) / (2 sab), tg = sign(zeta) / (|zeta| + sqrt(1 + zeta^2))
+    const double d = sbb - saa;
+    const double tg = 2.0 * sab / (d + copysign(sqrt(d * d + 4.0 * sab * sab), d));
+    const double cs = lin_rsqrt(1.0 + tg * tg), sn = cs * tg;
+    for (int i = lane; i < Ls; i += 32) {
+        const double x = ra[i], y = rb[i];
+        ra[i] = cs * x - sn * y;
+        rb[i] = sn * x + cs * y;
+    }
+    return true;
+}
+
+// block one-sided Jacobi on the rows of G (K x K) with accumulator Jt (K x Mj), both row-major in global memory.
+// Ends with a grid barrier (all rows globally visible).  Returns the number of sweeps.
+TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flags, long long* tm) {
+    const int nb = c.p.nb, Ls = K + Mj, lane = c.lane, wid = c.wid, nw = c.nw;
+    const int nblk = (K + nb - 1) / nb, nbe = nblk + (nblk & 1), npairs = nbe / 2, rounds = nbe - 1;
+    const double tol = 2.220446049250313e-16 * sqrt((double)K), tol2 = tol * tol;
+    int* rotated = (int*)(c.smem + 36);
+    double* rowsS = c.smem + c.p.oTaus;
+    int sweeps = 0;
+    if (K < 2) return 0;
+    for (; sweeps < 60; ++sweeps) {
+        for (int t = 0; t < rounds; ++t) {
+            for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
+                int a, b;
+                if (pi == 0) {
+                    a = nbe - 1;
+                    b = t;
+                } else {
+                    a = (t + pi) % (nbe - 1);
+                    b = (t - pi + nbe - 1) % (nbe - 1);
+                }
+                if (a > b) { const int q = a; a = b; b = q; }       // a < b, only b can be the phantom block
+                const bool bvalid = b < nblk;
+                if (!bvalid && t != 0) continue;
+                const int na = imin(nb, K - a * nb), nbb = bvalid ? imin(nb, K - b * nb) : 0;
+                const long long t0 = lin_now();
+                __syncthreads();
+                if (threadIdx.x == 0) *rotated = 0;
+                for (int slot = wid; slot < 2 * nb; slot += nw) {      // slot q < nb -> block a, nb + q -> block b
+                    const int q = slot % nb, blk = slot < nb ? a : b, cnt = slot < nb ? na : nbb;
+                    if (q >= cnt) continue;
+                    const long row = (long)blk * nb + q;
+                    double* dstr = rowsS + (long)slot * Ls;
+                    for (int i = lane; i < K; i += 32) dstr[i] = ld_cg(G + row * K + i);
+                    for (int i = lane; i < Mj; i += 32) dstr[K + i] = ld_cg(Jt + row * Mj + i);
+                }
+                __syncthreads();
+                const long long t1 = lin_now();
+                bool rot = false;
+                if (t == 0 && nb > 1) {
+                    // intra-block pairs of both blocks: round-robin over the nb (even) slots of each block
+                    const int half = nb / 2;
+                    for (int u = 0; u < nb - 1; ++u) {
+                        for (int task = wid; task < 2 * half; task += nw) {
+                            const int sel = task / half, q = task % half;
+                            const int cnt = sel == 0 ? na : nbb;
+                            int x, y;
+                            if (q == 0) {
+                                x = nb - 1;
+                                y = u;
+                            } else {
+                                x = (u + q) % (nb - 1);
+                                y = (u - q + nb - 1) % (nb - 1);
+                            }
+                            if (x >= cnt || y >= cnt) continue;
+                            if (x > y) { const int z = x; x = y; y = z; }
+                            rot |= lin_jacobi_pair(rowsS + (long)(sel * nb + x) * Ls, rowsS + (long)(sel * nb + y) * Ls, K, Ls,
+                                                   tol2, lane);
+                        }
+                        __syncthreads();
+                    }
+                }
+                if (bvalid) {
+                    for (int u = 0; u < nb; ++u) {
+                        for (int i = wid; i < nb; i += nw) {
+                            const int jb = (i + u) % nb;
+                            if (i >= na || jb >= nbb) continue;
+                            rot |= lin_jacobi_pair(rowsS + (long)i * Ls, rowsS + (long)(nb + jb) * Ls, K, Ls, tol2, lane);
+                        }
+                        __syncthreads();
+                    }
+                }
+                if (rot && lane == 0) *rotated = 1;
+                __syncthreads();
+                const long long t2 = lin_now();
+                if (*rotated) {
+                    for (int slot = wid; slot < 2 * nb; slot += nw) {
+                        const int q = slot % nb, blk = slot < nb ? a : b, cnt = slot < nb ? na : nbb;
+                        if (q >= cnt) continue;
+                        const long row = (long)blk * nb + q;
+                        const double* srcr = rowsS + (long)slot * Ls;
+                        for (int i = lane; i < K; i += 32) G[row * K + i] = srcr[i];
+                        for (int i = lane; i < Mj; i += 32) Jt[row * Mj + i] = srcr[K + i];
+                    }
+                    if (threadIdx.x == 0) flags[sweeps] = 1;
+                }
+                tm[0] += t1 - t0;
+                tm[1] += t2 - t1;
+                tm[2] += lin_now() - t2;
+            }
+            const long long t3 = lin_now();
+            c.sync();
+            tm[3] += lin_now() - t3;
+        }
+        if (ld_cg_i(&flags[sweeps]) == 0) {
+            ++sweeps;
+            break;
+        }
     }
     return sweeps;
 }
 
-struct SvdParams {
-    const double* A;
-    long a_rs, a_cs, a_bs;
-    int M, N;
-    double* U;      // batch x M x K row-major
-    double* S;      // batch x K
-    double* Wt;     // batch x K x N row-major  (S * V^T)
-    double* ws;     // batch x ws_per
-    long ws_per;
-    int use_smem;
-    int* info;      // batch: sweeps used
-};
-
-TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_svd_left(const SvdParams p) {
+// grid = (CTAs per matrix, batch)
+TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_linalg(const LinParams p) {
     TT_SMEM_DECL(smem_raw);
     double* smem = (double*)smem_raw;
-    const int M = p.M, N = p.N, K = imin(M, N);
-    const bool tall = M > N;
-    double* scr = smem;
-    int* flag = (int*)(smem + 36);
-    double* base = p.use_smem ? smem + 40 : p.ws + blockIdx.x * p.ws_per;
-    // workspace layout: G (K x N) | Jt (K x K) | sv (K) | ord (K ints, in doubles) | [tall: W (M x N) | tau (K) | Q (M x K)]
-    double* G = base;
-    double* Jt = G + (long)K * N;
-    double* sv = Jt + (long)K * K;
-    int* ord = (int*)(sv + K);
-    double* W = sv + K + (K + 1) / 2 + 1;
-    double* tau = W + (long)M * N;
-    double* Q = tau + K;
-    const double* A = p.A + blockIdx.x * p.a_bs;
-    if (tall) {
-        for (int i = threadIdx.x; i < M * N; i += blockDim.x) {
-            const int row = i / N, c = i % N;
-            W[row + (long)c * M] = A[row * p.a_rs + c * p.a_cs];
-        }
-        __syncthreads();
-        qr_factor(W, tau, M, N, scr);
-        for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
-            const int row = i / N, c = i % N;
-            G[i] = row <= c ? W[row + (long)c * M] : 0.0;
-        }
-        qr_form_q(W, tau, M, N, Q, K, 1);
-    } else {
-        for (int i = threadIdx.x; i < M * N; i += blockDim.x) G[i] = A[(i / N) * p.a_rs + (i % N) * p.a_cs];
+    const int batch = blockIdx.y;
+    int* flags = (int*)(p.ws + (long)batch * 40);
+    LinCtx c(p, smem, (unsigned*)(flags + 64));
+    double* ws = p.ws + (long)p.nbatch * 40 + (long)batch * p.ws_per;
+    const double* A = p.A + (long)batch * p.a_bs;
+    const int M = p.M, N = p.N, K = imin(M, N), M1 = p.M1, Mj = p.Mj;
+    const bool wide = p.mode == 0 && M < N;
+    double* W1 = ws + p.oW1;
+    double* tau1 = ws + p.oTau1;
+    double* W2 = ws + p.oW2;
+    double* tau2 = ws + p.oTau2;
+    double* G = ws + p.oG;
+    double* Jt = ws + p.oJt;
+    double* sv = ws + p.oSv;
+    double* U = p.U + (long)batch * M * K;
+    double* Wt = p.Wt + (long)batch * K * N;
+    const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gth = (long)gridDim.x * blockDim.x;
+    const long long t_start = lin_now();
+    long long tm[4] = {0, 0, 0, 0};
+
+    // working copy, column-major: A (M x N), or A^T (N x M) for a wide SVD
+    for (long i = gtid; i < (long)M * N; i += gth) {
+        const long row = i / N, col = i % N;
+        const double v = A[row * p.a_rs + col * p.a_cs];
+        if (!wide) W1[row + col * M] = v;
+        else W1[col + row * N] = v;
     }
-    for (int i = threadIdx.x; i < K * K; i += blockDim.x) Jt[i] = (i / K == i % K) ? 1.0 : 0.0;
-    __syncthreads();
-    const int sweeps = jacobi_rows(G, Jt, K, N, flag);
-    // singular values = row norms; sort descending (stable rank by counting)
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int i = wid; i < K; i += nw) {
+    c.sync();
+    lin_qr_factor(c, W1, tau1, M1, p.N1);
+    if (p.mode == 1) {
+        for (long i = gtid; i < (long)K * N; i += gth) {
+            const long row = i / N, col = i % N;
+            Wt[i] = row <= col ? ld_cg(W1 + row + col * M) : 0.0;
+        }
+        lin_apply_q(c, W1, tau1, M, K, K, 0, nullptr, nullptr, U, 1, K);      // column t of Q -> Q (M x K) row-major
+        return;
+    }
+    const double* Wq = W1;      // factor whose R is rotated and whose Q^T seeds the accumulator
+    const double* tq = tau1;
+    int Mq = M1;
+    if (wide) {
+        // L = R1^T (K x K lower triangular), column-major working copy, second QR
+        for (long i = gtid; i < (long)K * K; i += gth) {
+            const long row = i % K, col = i / K;
+            W2[i] = col <= row ? ld_cg(W1 + col + row * M1) : 0.0;
+        }
+        c.sync();
+        lin_qr_factor(c, W2, tau2, K, K);
+        Wq = W2;
+        tq = tau2;
+        Mq = K;
+    }
+    const long long t_qr = lin_now();
+    for (long i = gtid; i < (long)K * K; i += gth) {
+        const long row = i / K, col = i % K;
+        G[i] = row <= col ? ld_cg(Wq + row + col * Mq) : 0.0;
+    }
+    lin_apply_q(c, Wq, tq, Mq, K, K, 0, nullptr, nullptr, Jt, Mj, 1);          // rows of Q^T (K x Mq), Mj == Mq
+    c.sync();
+    const long long t_q = lin_now();
+    const int sweeps = lin_jacobi(c, G, Jt, K, Mj, flags, tm);
+    const long long t_jac = lin_now();
+    // singular values = row norms
+    for (int i = c.gw; i < K; i += c.GW) {
         double s = 0.0;
-        for (int c = lane; c < N; c += 32) s += G[(long)i * N + c] * G[(long)i * N + c];
+        for (int q = c.lane; q < K; q += 32) {
+            const double g = ld_cg(G + (long)i * K + q);
+            s += g * g;
+        }
         s = warp_sum(s);
-        if (lane == 0) sv[i] = sqrt(s);
+        if (c.lane == 0) sv[i] = sqrt(s);
     }
+    c.sync();
+    // descending order (stable counting rank), computed redundantly by every CTA in shared memory
+    int* ord = (int*)(smem + p.oOrd);
+    double* svS = smem + p.oSvS;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) svS[i] = ld_cg(sv + i);
     __syncthreads();
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
         int rank = 0;
-        const double si = sv[i];
-        for (int j = 0; j < K; ++j) rank += (sv[j] > si || (sv[j] == si && j < i)) ? 1 : 0;
+        const double si = svS[i];
+        for (int j = 0; j < K; ++j) rank += (svS[j] > si || (svS[j] == si && j < i)) ? 1 : 0;
         ord[rank] = i;
     }
     __syncthreads();
-    double* S = p.S + (long)blockIdx.x * K;
-    double* Wt = p.Wt + (long)blockIdx.x * K * N;
-    double* U = p.U + (long)blockIdx.x * M * K;
-    for (int i = threadIdx.x; i < K; i += blockDim.x) S[i] = sv[ord[i]];
-    for (int i = threadIdx.x; i < K * N; i += blockDim.x) Wt[i] = G[(long)ord[i / N] * N + i % N];
-    if (!tall) {
-        for (int i = threadIdx.x; i < M * K; i += blockDim.x) U[i] = Jt[(long)ord[i % K] * K + i / K];
+    double* S = p.S + (long)batch * K;
+    for (long i = gtid; i < K; i += gth) S[i] = svS[ord[i]];
+    for (long i = gtid; i < (long)M * K; i += gth) U[i] = ld_cg(Jt + (long)ord[i % K] * Mj + i / K);
+    if (!wide) {
+        for (long i = gtid; i < (long)K * N; i += gth) Wt[i] = ld_cg(G + (long)ord[i / N] * K + i % N);
     } else {
-        // U[:, p] = Q * J[:, ord[p]]
-        for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
-            const int row = i / K, pcol = i % K;
-            const double* jt = Jt + (long)ord[pcol] * K;
-            const double* q = Q + (long)row * K;
-            double acc = 0.0;
-            for (int k = 0; k < K; ++k) acc += q[k] * jt[k];
-            U[i] = acc;
-        }
+        lin_apply_q(c, W1, tau1, M1, K, K, 1, G, ord, Wt, N, 1);               // W rows = Q1 [g; 0]
     }
-    if (threadIdx.x == 0 && p.info) p.info[blockIdx.x] = sweeps;
+    if (gtid == 0 && p.info) {
+        // [0] sweeps; ns: [1] QR(s), [2] Q^T set-up, [3] Jacobi, [4] grid, [5] block rows,
+        // Jacobi breakdown on CTA 0 (ns): [6] row loads, [7] rotations, [8] row stores, [9] grid barriers; [10] total
+        int* info = p.info + 16 * batch;
+        info[0] = sweeps;
+        info[1] = (int)(t_qr - t_start);
+        info[2] = (int)(t_q - t_qr);
+        info[3] = (int)(t_jac - t_q);
+        info[4] = (int)gridDim.x;
+        info[5] = p.nb;
+        info[6] = (int)tm[0];
+        info[7] = (int)tm[1];
+        info[8] = (int)tm[2];
+        info[9] = (int)tm[3];
+        info[10] = (int)(lin_now() - t_start);
+    }
 }
 
-static long svd_ws_doubles(int M, int N) {
-    const long K = M < N ? M : N;
-    long n = K * N + K * K + K + (K + 1) / 2 + 1;
-    if (M > N) n += (long)M * N + K + (long)M * K;
-    return n + 8;
+static int g_coop_min_dim = 17;
+
+struct LinPlan {
+    LinParams p;
+    int grid;
+    long smem_bytes;
+    long ws_total;
+};
+
+// shapes, workspace carve-up, shared-memory layout and grid of one call; returns 0 or an error code
+static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
+    LinParams& p = pl.p;
+    const long K = imin(M, N);
+    const bool wide = mode == 0 && M < N;
+    p.M = M; p.N = N; p.mode = mode; p.nbatch = nbatch;
+    p.M1 = wide ? N : M;
+    p.N1 = wide ? M : N;
+    p.Mj = wide ? (int)K : M;
+    long o = 0;
+    p.oW1 = o; o += (long)M * N;
+    p.oTau1 = o; o += K;
+    p.oW2 = o; o += wide ? K * K : 0;
+    p.oTau2 = o; o += wide ? K : 0;
+    p.oG = o; o += mode == 0 ? K * K : 0;
+    p.oJt = o; o += mode == 0 ? K * p.Mj : 0;
+    p.oSv = o; o += K;
+    p.ws_per = o + (o & 1);
+    pl.ws_total = (long)nbatch * 40 + (long)nbatch * p.ws_per;
+    DevInfo di = dev_info();
+    const int nw = block_threads() / 32;
+    p.ldp = p.M1 + (p.M1 & 1);
+    p.oOrd = 40;
+    p.oSvS = p.oOrd + (int)(K + 1) / 2 + 1;
+    p.oTaus = p.oSvS + (int)K;
+    p.oP = p.oTaus + TT_QR_PB;
+    const long Ls = K + p.Mj;
+    const long qr_doubles = p.oP + (long)TT_QR_PB * p.ldp;
+    int nb = 8;
+    while (nb > 1 && (p.oTaus + 2L * nb * Ls) * 8 > di.smem_optin - 1024) nb /= 2;
+    p.nb = nb;
+    const long jac_doubles = mode == 0 ? p.oTaus + 2L * nb * Ls : 0;
+    pl.smem_bytes = 8 * (qr_doubles > jac_doubles ? qr_doubles : jac_doubles);
+    if (pl.smem_bytes > di.smem_optin)
+        return fail(4, "linalg: %d x %d does not fit the kernel's shared memory (%ld B)", M, N, pl.smem_bytes);
+    int G = 1;
+    if (nbatch == 1 && K >= g_coop_min_dim && K >= 2) {
+        const int nblk = (int)((K + nb - 1) / nb), npairs = (nblk + 1) / 2;
+        G = imax(npairs, (int)((K + nw - 1) / nw));
+        if (g_coop_min_dim <= 1) G = imax(G, 2);        // forced (tests): always exercise the multi-CTA path
+        G = imax(1, imin(G, imin(64, di.sms)));
+    }
+    pl.grid = G;
+    return 0;
+}
+
+static int lin_launch(int mode, const double* A, long a_rs, long a_cs, long a_bs, int M, int N, double* U, double* S,
+                      double* Wt, double* ws, int* info, int nbatch, tt_stream_t st) {
+    LinPlan pl;
+    int rc = lin_plan(pl, mode, M, N, nbatch);
+    if (rc) return rc;
+    LinParams& p = pl.p;
+    p.A = A; p.a_rs = a_rs; p.a_cs = a_cs; p.a_bs = a_bs;
+    p.U = U; p.S = S; p.Wt = Wt; p.info = info; p.ws = ws;
+    if (dev_memset(ws, 0, (size_t)nbatch * 40 * 8, st)) return fail(5, "linalg: memset failed");
+    int G = pl.grid;
+#ifndef TTIPM_EMU
+    if (G > 1) {
+        DevInfo di = dev_info();
+        static int optin_done = 0;
+        if (!optin_done) {
+            cudaFuncSetAttribute((const void*)k_linalg, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
+            optin_done = 1;
+        }
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linalg, block_threads(), (size_t)pl.smem_bytes);
+        if (per_sm < 1) return fail(4, "linalg: kernel does not fit on an SM with %ld B shared memory", pl.smem_bytes);
+        if (G > per_sm * di.sms) G = per_sm * di.sms;
+    }
+#endif
+    return launch_kernel("k_linalg", k_linalg, dim3(G, nbatch), dim3(block_threads()), (size_t)pl.smem_bytes, st, G > 1, p);
 }
 
 }  // namespace ttipm
 
 using namespace ttipm;
 
+extern "C" int ttipm_linalg_coop_min_dim(int min_dim) {
+    const int old = g_coop_min_dim;
+    if (min_dim > 0) g_coop_min_dim = min_dim;
+    return old;
+}
+
 extern "C" int64_t ttipm_qr_workspace(int M, int N, int nbatch) {
-    return (int64_t)nbatch * ((int64_t)M * N + (M < N ? M : N));
+    LinPlan pl;
+    if (M < 1 || N < 1 || nbatch < 1 || lin_plan(pl, 1, M, N, nbatch)) return 0;
+    return pl.ws_total;
 }
 
 extern "C" int ttipm_qr(const double* A, int64_t a_rs, int64_t a_cs, int64_t a_bs, int M, int N, double* Q, double* R,
                         double* workspace, int nbatch, void* stream) {
     if (M < 1 || N < 1 || nbatch < 1) return fail(1, "qr: bad dims %d x %d", M, N);
-    QrParams p{A, (long)a_rs, (long)a_cs, (long)a_bs, M, N, Q, R, workspace, 0};
-    const long need = ((long)M * N + imin(M, N) + 40) * 8;
-    DevInfo di = dev_info();
-    p.use_smem = need <= di.smem_optin;
-    if (!p.use_smem && !workspace) return fail(1, "qr: %d x %d needs a workspace", M, N);
-    return launch_kernel("k_qr", k_qr, dim3(nbatch), dim3(block_threads()), p.use_smem ? need : 40 * 8,
-                         (tt_stream_t)stream, false, p);
+    if (!workspace) return fail(1, "qr: workspace required (ttipm_qr_workspace doubles)");
+    return lin_launch(1, A, (long)a_rs, (long)a_cs, (long)a_bs, M, N, Q, nullptr, R, workspace, nullptr, nbatch,
+                      (tt_stream_t)stream);
 }
 
-extern "C" int64_t ttipm_svd_workspace(int M, int N, int nbatch) { return (int64_t)nbatch * svd_ws_doubles(M, N); }
+extern "C" int64_t ttipm_svd_workspace(int M, int N, int nbatch) {
+    LinPlan pl;
+    if (M < 1 || N < 1 || nbatch < 1 || lin_plan(pl, 0, M, N, nbatch)) return 0;
+    return pl.ws_total;
+}
 
 extern "C" int ttipm_svd_left(const double* A, int64_t a_rs, int64_t a_cs, int64_t a_bs, int M, int N, double* U,
                               double* S, double* Wt, double* workspace, int32_t* info, int nbatch, void* stream) {
     if (M < 1 || N < 1 || nbatch < 1) return fail(1, "svd_left: bad dims %d x %d", M, N);
-    SvdParams p{A, (long)a_rs, (long)a_cs, (long)a_bs, M, N, U, S, Wt, workspace, svd_ws_doubles(M, N), 0, info};
-    const long need = (p.ws_per + 40) * 8;
-    DevInfo di = dev_info();
-    p.use_smem = need <= di.smem_optin;
-    if (!p.use_smem && !workspace) return fail(1, "svd_left: %d x %d needs a workspace", M, N);
-    return launch_kernel("k_svd_left", k_svd_left, dim3(nbatch), dim3(block_threads()), p.use_smem ? need : 40 * 8,
-                         (tt_stream_t)stream, false, p);
+    if (!workspace) return fail(1, "svd_left: workspace required (ttipm_svd_workspace doubles)");
+    return lin_launch(0, A, (long)a_rs, (long)a_cs, (long)a_bs, M, N, U, S, Wt, workspace, info, nbatch,
+                      (tt_stream_t)stream);
 }

@@ -43,6 +43,7 @@ SIGNATURES = {
     "ttipm_local_lgmres": (C.c_int, [C.c_int] + [C.POINTER(Term)] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, i64, C.c_int, C.c_int, C.c_int, C.c_double,
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ttipm_linalg_coop_min_dim": (C.c_int, [C.c_int]),
     "ttipm_qr_workspace": (i64, [C.c_int, C.c_int, C.c_int]),
     "ttipm_qr": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                            C.c_void_p]),

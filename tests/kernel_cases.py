@@ -188,13 +188,23 @@ def case_lgmres(rt, case, grid_hint=0, restart=None, shift=8.0, rtol=1e-5, max_i
     return errs, dict(its=int(info[0]), ref_its=ref.its, reason=int(info[2]), grid=int(info[5]), cycles=int(info[3]))
 
 
-def case_qr_svd(rt, shapes=((7, 5), (5, 7), (6, 6), (12, 3), (3, 12), (1, 4), (4, 1), (20, 12))):
-    """QR / left-SVD parity (gauge-aware): reconstruction, orthogonality, singular values."""
+def case_qr_svd(rt, shapes=((7, 5), (5, 7), (6, 6), (12, 3), (3, 12), (1, 4), (4, 1), (20, 12)), coop_min_dim=None,
+                graded=False):
+    """QR / left-SVD parity (gauge-aware): reconstruction, orthogonality, singular values.
+    coop_min_dim forces the cooperative multi-CTA kernel for matrices with min(M, N) >= that value."""
+    if coop_min_dim is not None:
+        old = rt.lib.ttipm_linalg_coop_min_dim(int(coop_min_dim))
+        try:
+            return case_qr_svd(rt, shapes, None, graded)
+        finally:
+            rt.lib.ttipm_linalg_coop_min_dim(old)
     import scipy.linalg as sla
     rng = np.random.default_rng(11)
     errs = {}
     for (M, N) in shapes:
         a = rng.standard_normal((M, N))
+        if graded:                              # singular values spanning 16 decades, like a TT unfolding before truncation
+            a = a * np.logspace(0, -16, N)[None, :]
         if M >= 6 and N >= 5:
             a[:, -1] = a[:, 0] * 2.0            # exactly rank deficient: zero singular value
         Kk = min(M, N)

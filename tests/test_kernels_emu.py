@@ -53,6 +53,13 @@ def test_qr_svd(rt):
     KC.assert_small(KC.case_qr_svd(rt), tol=1e-12)
 
 
+def test_qr_svd_cooperative(rt):
+    """the multi-CTA panel-QR / block-Jacobi kernel forced onto small shapes (2 emulated SMs)"""
+    shapes = ((7, 5), (5, 7), (6, 6), (12, 3), (3, 12), (1, 4), (4, 1), (20, 12), (37, 23), (19, 40), (24, 24))
+    KC.assert_small(KC.case_qr_svd(rt, shapes=shapes, coop_min_dim=1), tol=1e-12)
+    KC.assert_small(KC.case_qr_svd(rt, shapes=((37, 23), (19, 40)), coop_min_dim=1, graded=True), tol=1e-12)
+
+
 def test_elementwise(rt):
     KC.assert_small(KC.case_elementwise(rt), tol=1e-13)
 

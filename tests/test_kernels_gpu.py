@@ -76,6 +76,16 @@ def test_qr_svd(rt):
                                                (88, 66), (220, 165), (165, 220), (40, 300))), tol=1e-11)
 
 
+def test_qr_svd_cooperative(rt):
+    """multi-CTA panel QR + block Jacobi: forced onto small shapes, default dispatch at the AMEn truncation sizes
+    (maxcut_13 rank 2: (4 R) x (3 r) up to ~440 x 330), graded spectra, > 512 rows (memory-resident reflector path)"""
+    small = ((7, 5), (5, 7), (6, 6), (12, 3), (3, 12), (1, 4), (4, 1), (20, 12), (37, 23), (19, 40), (24, 24))
+    KC.assert_small(KC.case_qr_svd(rt, shapes=small, coop_min_dim=1), tol=1e-12)
+    big = ((88, 66), (220, 165), (165, 220), (440, 330), (330, 440), (400, 400), (600, 200), (64, 900))
+    KC.assert_small(KC.case_qr_svd(rt, shapes=big), tol=1e-11)
+    KC.assert_small(KC.case_qr_svd(rt, shapes=((440, 330), (165, 220), (600, 200)), graded=True), tol=1e-11)
+
+
 def test_elementwise(rt):
     KC.assert_small(KC.case_elementwise(rt), tol=1e-13)
 
