@@ -196,6 +196,11 @@ int ttipm_amen_core_shape(ttipm_amen* h, int k, int32_t* dims /* r, nb|0, n, R *
 int ttipm_amen_get_core(ttipm_amen* h, int k, double* dst_host);
 /* profile != 0: time every Krylov-kernel launch of the next run() with CUDA events (read back through stats) */
 int ttipm_amen_set_profile(ttipm_amen* h, int on);
+/* Per-category profile of the last profiled run (call ttipm_amen_stats first): out[27], 3 per category =
+ * seconds between the CUDA events bracketing the category's launches, algorithmic work (flops; bytes for the
+ * memory-bound helpers), launches.  Categories: 0 block matvec (K1), 1 interface update (K2), 2 rhs contraction (K3),
+ * 3 bond GEMM (K5), 4 QR, 5 SVD, 6 memory-bound helpers, 7 dense Schur fallback (cuSOLVER/cuBLAS), 8 Krylov kernel. */
+int ttipm_amen_profile(ttipm_amen* h, double* out);
 /* stats[12] = sweeps, local solves, dense solves, Krylov solves, Krylov inner steps, Krylov matvecs, kernel
  * launches, host syncs, peak device bytes, trace rows, seconds inside the Krylov kernel (profiling runs only), its
  * algorithmic flops; trace: 5 doubles (swp, k, res_old, res_new, r*R) per solve */

@@ -15,7 +15,7 @@ import subprocess
 import sys
 import tempfile
 
-REF = "/root/reference"
+REF = os.environ.get("TTIPM_REF_TREE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.abspath(os.path.join(HERE, "..", "_ref"))
 
@@ -35,11 +35,11 @@ setup(ext_modules=cythonize([
 
 
 def build(force=False):
-    if not os.path.isdir(REF):
-        return False
     dst = os.path.join(OUT, "cy_src")
     if not force and len(glob.glob(os.path.join(dst, "*.so"))) == 2:
         return True
+    if not os.path.isdir(os.path.join(REF, "cy_src")):
+        return False
     os.makedirs(dst, exist_ok=True)
     with tempfile.TemporaryDirectory(prefix="ttipm_ref_") as tmp:
         os.makedirs(os.path.join(tmp, "cy_src"))

@@ -11,7 +11,9 @@ import os
 import sys
 import types
 
-REF = "/root/reference"
+# TTIPM_REF_TREE: a maintainer's own checkout of the reference (e.g. on a machine that has both the
+# reference tree and a B200); default is the read-only mount of the build container
+REF = os.environ.get("TTIPM_REF_TREE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.abspath(os.path.join(HERE, "..", "_ref"))
 _loaded = None

@@ -32,7 +32,15 @@ def main():
     with use_runtime(rt):
         done = dropin.install()
         print("rebound:", {k: len(v) for k, v in done.items()}, flush=True)
+        if "--profile" in sys.argv:
+            import cProfile
+            import pstats
+            pr = cProfile.Profile()
+            pr.enable()
         out["dropin"] = run_ref_ipm.run(problem, dim, rank, seed, verbose="--verbose" in sys.argv)
+        if "--profile" in sys.argv:
+            pr.disable()
+            pstats.Stats(pr).sort_stats("cumulative").print_stats(70)
     print("DROPIN", json.dumps(out["dropin"]), flush=True)
     for i, a in enumerate(sys.argv):
         if a == "--out":

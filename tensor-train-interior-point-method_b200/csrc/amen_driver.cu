@@ -20,6 +20,34 @@ namespace ttipm {
 namespace drv {
 
 // ---------------------------------------------------------------------------------------------------
+// per-launch profile (profiling passes only)
+// ---------------------------------------------------------------------------------------------------
+ProfScope::ProfScope(Ctx& ctx, int cat, double work) : c(ctx), on(ctx.prof) {
+#ifndef TTIPM_EMU
+    if (!on) return;
+    ProfRec r;
+    r.cat = cat;
+    r.work = work;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    r.e0 = a;
+    r.e1 = b;
+    cudaEventRecord(a, c.st);
+    idx = c.recs.size();
+    c.recs.push_back(r);
+#else
+    (void)cat; (void)work;
+    on = false;
+#endif
+}
+ProfScope::~ProfScope() {
+#ifndef TTIPM_EMU
+    if (on) cudaEventRecord((cudaEvent_t)c.recs[idx].e1, c.st);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------
 // memory and transfers
 // ---------------------------------------------------------------------------------------------------
 void* dev_alloc(Ctx& c, size_t bytes) {
@@ -107,6 +135,10 @@ static Tensor block_matvec(Ctx& c, const Terms& tl, const Tensor& x, bool rnbR, 
     const long x_rs = x.s[o], x_ns = rnbR ? x.s[o + 1] : x.s[o + 2], x_bs = rnbR ? x.s[o + 2] : x.s[o + 1];
     Tensor y = batched ? Tensor::empty(c, {B, l, (long)nb_out, n, L}) : Tensor::empty(c, {l, (long)nb_out, n, L});
     if (sumsq) *sumsq = Tensor::empty(c, {B, nb_out * L});
+    double work = 0.0;
+    for (const ttipm_term& t : tl.v)
+        work += (double)B * (2.0 * r * n * R * L * t.S + 2.0 * r * L * t.s * n * n * t.S + 2.0 * l * n * L * r * t.s);
+    ProfScope ps(c, CAT_MATVEC, work);
     check_rc(ttipm_block_matvec(tl.v.data(), (int)tl.v.size(), (int)l, (int)L, (int)r, (int)R, (int)n, nb_out, x.p, x_bs,
                                 x_rs, x_ns, batched ? x.s[0] : 0, y.p, n * L, nb_out * n * L, L, l * nb_out * n * L,
                                 y_scale, sub ? sub->p : nullptr, sub_scale, sumsq ? sumsq->p : nullptr, (int)B, c.st),
@@ -119,6 +151,7 @@ static Tensor local_diag_inv(Ctx& c, const Tensor& P1, const Tensor& A, const Te
     Terms t;
     t.add(P1, A, P2, 0, 0);
     Tensor out = Tensor::empty(c, {P1.d[0], A.d[1], P2.d[0]});
+    ProfScope ps(c, CAT_EWISE, 8.0 * (double)(P1.numel() + A.numel() + P2.numel() + out.numel()));
     check_rc(ttipm_local_diag(t.v.data(), (int)P1.d[0], (int)P2.d[0], (int)A.d[1], 1, out.p, c.st), "local_diag");
     c.launches++;
     return out;
@@ -129,6 +162,7 @@ static Tensor local_dense(Ctx& c, const Tensor& P1, const Tensor& A, const Tenso
     t.add(P1, A, P2, 0, 0);
     const long l = P1.d[0], r = P1.d[2], L = P2.d[0], R = P2.d[2], n = A.d[1];
     Tensor out = Tensor::empty(c, {l * n * L, r * n * R});
+    ProfScope ps(c, CAT_DENSE, 2.0 * (double)out.numel() * (double)(A.d[0] + A.d[3]));
     check_rc(ttipm_local_dense(t.v.data(), (int)l, (int)L, (int)r, (int)R, (int)n, out.p, c.st), "local_dense");
     c.launches++;
     return out;
@@ -147,6 +181,14 @@ static std::vector<Tensor> phi_update(Ctx& c, const std::vector<Tensor>& phis, c
         for (int i = 0; i < 4; ++i) t[q].a_strides[i] = cores[q].s[i];
         t[q].s = (int)s; t[q].S = (int)S;
     }
+    double work = 0.0;
+    for (size_t q = 0; q < n; ++q) {
+        const double s_ = (double)cores[q].d[0], S_ = (double)cores[q].d[3];
+        // 2 l s r N R + 2 l R s N M S + 2 l M L S R (forward), mirrored for the backward update
+        work += forward ? 2.0 * ul * s_ * vr * nm * vR + 2.0 * ul * vR * s_ * nm * nm * S_ + 2.0 * ul * nm * uL * S_ * vR
+                        : 2.0 * uL * S_ * vR * nm * vr + 2.0 * uL * vr * S_ * nm * nm * s_ + 2.0 * uL * nm * ul * s_ * vr;
+    }
+    ProfScope ps(c, CAT_PHI, work);
     check_rc(ttipm_phi_update(t.data(), (int)n, forward ? 1 : 0, U.p, (int)ul, (int)uL, V.p, (int)vr, (int)vR, (int)nm,
                               c.st), "phi_update");
     c.launches++;
@@ -165,6 +207,10 @@ static Tensor rhs_project(Ctx& c, const std::vector<Tensor>& X1, const std::vect
         t[q].out = out.p + rows[q] * out.s[1];
         t[q].b = (int)Bc[q].d[0]; t[q].Bp = (int)Bc[q].d[2];
     }
+    double work = 0.0;
+    for (size_t q = 0; q < rows.size(); ++q)
+        work += 2.0 * t[q].b * r * n * t[q].Bp + 2.0 * r * n * t[q].Bp * R;
+    ProfScope ps(c, CAT_RHS, work);
     check_rc(ttipm_rhs_contract(t.data(), (int)t.size(), 0, nullptr, (int)r, (int)R, (int)n, out.s[0], c.st), "rhs_project");
     c.launches++;
     return out;
@@ -183,6 +229,9 @@ static std::vector<Tensor> phi_rhs_update(Ctx& c, const std::vector<Tensor>& Xb,
         t[q].out = outs[q].p;
     }
     if (n) {
+        double work = 0.0;
+        for (size_t q = 0; q < n; ++q) work += 2.0 * r * nm * R * (forward ? t[q].b : t[q].Bp) + 2.0 * t[q].b * nm * t[q].Bp * (forward ? R : r);
+        ProfScope ps(c, CAT_RHS, work);
         check_rc(ttipm_rhs_contract(t.data(), (int)n, forward ? 1 : 2, core.p, (int)r, (int)R, (int)nm, 0, c.st),
                  "phi_rhs_update");
         c.launches++;
@@ -196,6 +245,7 @@ static Tensor gemm(Ctx& c, const Tensor& A, const Tensor& B) {
     const int o = batched ? 1 : 0;
     const long nb = batched ? A.d[0] : 1, M = A.d[o], K = A.d[o + 1], N = B.d[o + 1];
     Tensor C = batched ? Tensor::empty(c, {nb, M, N}) : Tensor::empty(c, {M, N});
+    ProfScope ps(c, CAT_GEMM, 2.0 * nb * M * N * K);
     check_rc(ttipm_gemm((int)M, (int)N, (int)K, 1.0, A.p, A.s[o], A.s[o + 1], batched && nb > 1 ? A.s[0] : 0, B.p, B.s[o],
                         B.s[o + 1], batched && nb > 1 ? B.s[0] : 0, 0.0, C.p, N, 1, M * N, (int)nb, c.st), "gemm");
     c.launches++;
@@ -207,6 +257,8 @@ static void qr(Ctx& c, const Tensor& A, Tensor& Q, Tensor& R) {
     Q = Tensor::empty(c, {M, K});
     R = Tensor::empty(c, {K, N});
     Tensor ws = Tensor::empty(c, {(long)ttipm_qr_workspace((int)M, (int)N, 1)});
+    // Householder QR with explicit Q (geqrf + orgqr): 4 M N K - (4/3) K^3
+    ProfScope ps(c, CAT_QR, 4.0 * M * N * K - 4.0 / 3.0 * K * K * K);
     check_rc(ttipm_qr(A.p, A.s[0], A.s[1], 0, (int)M, (int)N, Q.p, R.p, ws.p, 1, c.st), "qr");
     c.launches++;
 }
@@ -217,6 +269,8 @@ static void svd_left(Ctx& c, const Tensor& A, Tensor& U, Tensor& S, Tensor& W) {
     S = Tensor::empty(c, {K});
     W = Tensor::empty(c, {K, N});
     Tensor ws = Tensor::empty(c, {(long)ttipm_svd_workspace((int)M, (int)N, 1)});
+    // economy SVD with both factors, Golub & Van Loan R-SVD count: 6 m n^2 + 20 n^3 (m >= n)
+    ProfScope ps(c, CAT_SVD, 6.0 * std::max(M, N) * K * K + 20.0 * K * K * K);
     check_rc(ttipm_svd_left(A.p, A.s[0], A.s[1], 0, (int)M, (int)N, U.p, S.p, W.p, ws.p, nullptr, 1, c.st), "svd_left");
     c.launches++;
 }
@@ -227,6 +281,7 @@ static Tensor permute4(Ctx& c, const Tensor& x, int p0, int p1, int p2, int p3, 
     int32_t dims[4] = {(int32_t)x.d[0], (int32_t)x.d[1], (int32_t)x.d[2], (int32_t)x.d[3]};
     int32_t perm[4] = {p0, p1, p2, p3};
     Tensor out = Tensor::empty(c, {x.d[p0], x.d[p1], x.d[p2], x.d[p3]});
+    ProfScope ps(c, CAT_EWISE, 16.0 * (double)x.numel());
     check_rc(ttipm_permute4(x.p, dims, perm, out.p, scale ? scale->p : nullptr, axis, divide ? 2 : 1, c.st), "permute4");
     c.launches++;
     return out;
@@ -234,6 +289,7 @@ static Tensor permute4(Ctx& c, const Tensor& x, int p0, int p1, int p2, int p3, 
 
 static Tensor block_norms(Ctx& c, const Tensor& x) {
     Tensor out = Tensor::empty(c, {x.d[1]});
+    ProfScope ps(c, CAT_EWISE, 8.0 * (double)x.numel());
     check_rc(ttipm_block_norms(x.p, (int)x.d[0], (int)x.d[1], (int)(x.numel() / (x.d[0] * x.d[1])), 1e-10, out.p, c.st),
              "block_norms");
     c.launches++;
@@ -268,6 +324,7 @@ static void ewise(Ctx& c, const Tensor& a, double alpha, const Tensor* b, double
     long rows, inner, rs[5];
     panels(ts, 5, rows, inner, rs);
     if (sumsq) *sumsq = Tensor::empty(c, {256});
+    ProfScope ps(c, CAT_EWISE, 8.0 * (double)rows * inner * (1 + (b ? 1 : 0) + (cc ? 1 : 0) + (w ? 1 : 0) + (out ? 1 : 0)));
     check_rc(ttipm_ewise((int)rows, (int)inner, alpha, a.p, rs[0], beta, b ? b->p : nullptr, rs[1], gamma,
                          cc ? cc->p : nullptr, rs[2], w ? w->p : nullptr, rs[3], out ? out->p : nullptr, rs[4],
                          sumsq ? sumsq->p : nullptr, c.st), "ewise");
@@ -276,6 +333,7 @@ static void ewise(Ctx& c, const Tensor& a, double alpha, const Tensor* b, double
 
 static Tensor copy2d(Ctx& c, const Tensor& A) {     // contiguous copy of a strided 2-D view
     Tensor out = Tensor::empty(c, {A.d[0], A.d[1]});
+    ProfScope ps(c, CAT_EWISE, 16.0 * (double)out.numel());
     check_rc(ttipm_scale2d(A.p, A.s[0], A.s[1], (int)A.d[0], (int)A.d[1], nullptr, 0, 0, out.p, c.st), "copy2d");
     c.launches++;
     return out;
@@ -365,6 +423,7 @@ struct Dense {
 #else
         // row-major C = A B  <=>  column-major C^T = B^T A^T
         const long lda = ta ? M : K, ldb = tb ? K : N;
+        ProfScope ps(c, CAT_DENSE, 2.0 * M * N * K);
         if (cublasDgemm(blas, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, (int)N, (int)M, (int)K, &alpha,
                         B, (int)ldb, A, (int)lda, &beta, C, (int)N) != CUBLAS_STATUS_SUCCESS)
             throw DriverError(93, "cublasDgemm failed");
@@ -388,6 +447,7 @@ struct Dense {
         }
         return true;
 #else
+        ProfScope ps(c, CAT_DENSE, (double)m * m * m / 3.0);
         int lwork = 0;
         cusolverDnDpotrf_bufferSize(sol, CUBLAS_FILL_MODE_UPPER, (int)m, A, (int)m, &lwork);
         Tensor work = Tensor::empty(c, {(long)lwork + 2});
@@ -420,6 +480,7 @@ struct Dense {
 #else
         // column-major view: B^T (k x m), factor U = L^T upper with A = U^T U; solve X^T U^T U = B^T from the right
         const double one = 1.0;
+        ProfScope ps(c, CAT_DENSE, 2.0 * m * m * k);
         if (cublasDtrsm(blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)k, (int)m,
                         &one, Lc, (int)m, B, (int)k) != CUBLAS_STATUS_SUCCESS ||
             cublasDtrsm(blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)k, (int)m,
@@ -452,6 +513,7 @@ struct Dense {
             }
         }
 #else
+        ProfScope ps(c, CAT_DENSE, 2.0 * m * m * m / 3.0);
         int lwork = 0;
         cusolverDnDgetrf_bufferSize(sol, (int)m, (int)m, f.a.p, (int)m, &lwork);
         Tensor work = Tensor::empty(c, {(long)lwork + 2});
@@ -487,6 +549,7 @@ struct Dense {
         Tensor Bt = k == 1 ? Tensor::empty(c, {m, 1}) : copy2d(c, B.t2());
         if (k == 1) dev_to_dev(c, B.p, (size_t)m, Bt.p);
         Tensor info = Tensor::empty(c, {2});
+        ProfScope ps(c, CAT_DENSE, 2.0 * m * m * k);
         if (cusolverDnDgetrs(sol, CUBLAS_OP_T, (int)m, (int)k, f.a.p, (int)m, (const int*)f.piv.p, Bt.p, (int)m,
                              (int*)info.p) != CUSOLVER_STATUS_SUCCESS)
             throw DriverError(93, "getrs failed");
@@ -531,6 +594,7 @@ struct Amen {
     std::vector<LgProf> lg_prof;               // one record per Krylov solve (same order as lg_infos)
     bool profile = false, stats_done = false;
     double lg_time = 0.0, lg_flops = 0.0;
+    double cat_seconds[CAT_COUNT] = {0}, cat_work[CAT_COUNT] = {0}, cat_launches[CAT_COUNT] = {0};
     std::string error;
 
     Tensor ones(std::initializer_list<long> dims) {
@@ -750,6 +814,7 @@ struct Amen {
             Tensor ws = Tensor::empty(c, {(long)ttipm_lgmres_workspace(ineq, (int)r, (int)R, (int)n, restart, aug)});
             auto lg = [&](const Tensor& in, bool apply_only, Tensor* info) {
                 Tensor out = Tensor::empty(c, {(long)nred, r, n, R});
+                ProfScope ps(c, CAT_KRYLOV, 0.0);         // work is known after the solve (inner steps): see lg_flops
                 check_rc(ttipm_local_lgmres(ineq, T + 0, T + 1, T + 2, T + 3, ineq ? T + 4 : nullptr, ineq ? T + 5 : nullptr,
                                             inv_I.p, (int)r, (int)R, (int)n, in.p, out.p, ws.p, ws.numel(), restart, aug, 300,
                                             rtol, apply_only ? 1 : 0, 0, info ? info->p : nullptr, c.st), "local_lgmres");
@@ -935,6 +1000,7 @@ struct Amen {
                                      .reshape({r0 - 1, r_k, n, (long)bs, R_k});
                     Tensor Y = block_matvec(c, full, terms, !bck, bs, r_k, R_k, nullptr, 1.0, 0.0, nullptr);
                     Tensor parts = Tensor::empty(c, {r0 - 1, 256});
+                    ProfScope ps(c, CAT_EWISE, 8.0 * (double)(res.numel() + Y.numel()));
                     check_rc(ttipm_trunc_resnorms(res.p, Y.p, (int)(r0 - 1), res.numel(), parts.p, c.st), "trunc_resnorms");
                     c.launches++;
                     std::vector<double> ph = read_vec(c, parts);
@@ -1186,6 +1252,7 @@ extern "C" int ttipm_amen_run(ttipm_amen* h, double term_tol, int r_max, double 
         }
         a.trace.clear();
         a.stats_done = false;
+        a.c.prof = a.profile;
         const double res = a.run(term_tol, r_max, eps, nswp, direction);
         if (final_res) *final_res = res;
         if (sweeps) *sweeps = a.sweeps;
@@ -1213,6 +1280,21 @@ extern "C" int ttipm_amen_get_core(ttipm_amen* h, int k, double* dst_host) {
     });
 }
 
+// Per-category profile of the last run() made with set_profile(1): out[3 * cat + {0, 1, 2}] = seconds between the
+// CUDA events bracketing the category's launches, algorithmic work (flops; bytes for cat 6), launches.  Categories:
+// 0 block matvec, 1 interface update, 2 rhs contraction, 3 bond GEMM, 4 QR, 5 SVD, 6 memory-bound helpers,
+// 7 dense Schur fallback (cuSOLVER/cuBLAS), 8 Krylov kernel.  Call ttipm_amen_stats first (it resolves the events).
+extern "C" int ttipm_amen_profile(ttipm_amen* h, double* out) {
+    TT_TRY(h, {
+        Amen& a = h->a;
+        for (int q = 0; q < CAT_COUNT; ++q) {
+            out[3 * q] = a.cat_seconds[q];
+            out[3 * q + 1] = a.cat_work[q];
+            out[3 * q + 2] = a.cat_launches[q];
+        }
+    });
+}
+
 // stats[0..11]: [10] = seconds inside the Krylov kernel (only with profiling on), [11] = its algorithmic flops
 // stats[0..9] = sweeps, local solves, dense solves, Krylov solves, Krylov inner steps, Krylov matvecs, launches,
 //               host syncs, peak device bytes, trace rows; trace (may be NULL) receives 5 doubles per local solve
@@ -1237,7 +1319,21 @@ extern "C" int ttipm_amen_stats(ttipm_amen* h, double* stats, double* trace, int
                 }
 #endif
             }
+#ifndef TTIPM_EMU
+            for (const ProfRec& r : a.c.recs) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, (cudaEvent_t)r.e0, (cudaEvent_t)r.e1);
+                a.cat_seconds[r.cat] += ms * 1e-3;
+                a.cat_work[r.cat] += r.work;
+                a.cat_launches[r.cat] += 1.0;
+                cudaEventDestroy((cudaEvent_t)r.e0);
+                cudaEventDestroy((cudaEvent_t)r.e1);
+            }
+#endif
+            a.c.recs.clear();
+            a.cat_work[CAT_KRYLOV] = a.lg_flops;
             a.profile = false;
+            a.c.prof = false;
             a.stats_done = true;
         }
         const double its = (double)a.lgmres_its, mv = (double)a.lgmres_matvecs;

@@ -42,6 +42,7 @@ struct LinParams {
     double* ws;          // [nbatch x 40 doubles: sweep flags + barrier][nbatch x ws_per]
     long ws_per;
     long oW1, oTau1, oW2, oTau2, oG, oJt, oSv;      // offsets inside one batch workspace
+    long oPg;            // >= 0: the reflector panel lives in the batch workspace (columns too long for shared memory)
     int M1, N1;          // first QR: M x N (tall, square, QR mode) or N x M (wide SVD, factors A^T)
     int Mj;              // accumulator row length
     int nb;              // Jacobi block rows
@@ -56,7 +57,9 @@ struct LinCtx {
     unsigned* barrier;
     unsigned epoch;
     int lane, wid, nw, gw, GW;
+    double* panel;       // TT_QR_PB reflector columns: shared memory, or global scratch for very tall matrices
     TT_DEVM LinCtx(const LinParams& pp, double* s, unsigned* bar) : p(pp), smem(s), barrier(bar), epoch(0) {
+        panel = s + pp.oP;
         lane = threadIdx.x & 31;
         wid = threadIdx.x >> 5;
         nw = blockDim.x >> 5;
@@ -123,7 +126,7 @@ TT_DEV void lin_load_panel(const double* W, const double* tau, int Mq, int j0, i
 TT_DEV void lin_qr_factor(LinCtx& c, double* W, double* tau, int Mq, int Nq) {
     const int K = imin(Mq, Nq), ldp = c.p.ldp, lane = c.lane, wid = c.wid, nw = c.nw;
     double* taus = c.smem + c.p.oTaus;
-    double* P = c.smem + c.p.oP;
+    double* P = c.panel;
     for (int p0 = 0; p0 < K; p0 += TT_QR_PB) {
         const int pw = imin(TT_QR_PB, K - p0), rows = Mq - p0;
         __syncthreads();
@@ -203,7 +206,7 @@ TT_DEV void lin_apply_q(LinCtx& c, const double* W, const double* tau, int Mq, i
                         const double* src, const int* ord, double* dst, long row_stride, long elem_stride) {
     const int ldp = c.p.ldp, lane = c.lane;
     double* taus = c.smem + c.p.oTaus;
-    double* P = c.smem + c.p.oP;
+    double* P = c.panel;
     const bool in_regs = Mq <= 32 * TT_LIN_REG;
     for (int base = 0; base < ntask; base += c.GW) {
         const int first = base + blockIdx.x * c.nw;
@@ -392,6 +395,7 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_linalg(const LinParams p) {
     int* flags = (int*)(p.ws + (long)batch * 40);
     LinCtx c(p, smem, (unsigned*)(flags + 64));
     double* ws = p.ws + (long)p.nbatch * 40 + (long)batch * p.ws_per;
+    if (p.oPg >= 0) c.panel = ws + p.oPg;
     const double* A = p.A + (long)batch * p.a_bs;
     const int M = p.M, N = p.N, K = imin(M, N), M1 = p.M1, Mj = p.Mj;
     const bool wide = p.mode == 0 && M < N;
@@ -525,17 +529,22 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
     p.oG = o; o += mode == 0 ? K * K : 0;
     p.oJt = o; o += mode == 0 ? K * p.Mj : 0;
     p.oSv = o; o += K;
-    p.ws_per = o + (o & 1);
-    pl.ws_total = (long)nbatch * 40 + (long)nbatch * p.ws_per;
     DevInfo di = dev_info();
     const int nw = block_threads() / 32;
     p.ldp = p.M1 + (p.M1 & 1);
+    // a panel of TT_QR_PB columns of M1 rows normally sits in shared memory; columns too long for that keep the
+    // panel in the workspace and the matrix is factored by one CTA (rare: unfoldings with > ~3000 rows)
+    const bool panel_global = (40L + (K + 1) / 2 + 1 + K + TT_QR_PB + (long)TT_QR_PB * p.ldp) * 8 > di.smem_optin - 1024;
+    p.oPg = -1;
+    if (panel_global) { p.oPg = o; o += (long)TT_QR_PB * p.ldp; }
+    p.ws_per = o + (o & 1);
+    pl.ws_total = (long)nbatch * 40 + (long)nbatch * p.ws_per;
     p.oOrd = 40;
     p.oSvS = p.oOrd + (int)(K + 1) / 2 + 1;
     p.oTaus = p.oSvS + (int)K;
     p.oP = p.oTaus + TT_QR_PB;
     const long Ls = K + p.Mj;
-    const long qr_doubles = p.oP + (long)TT_QR_PB * p.ldp;
+    const long qr_doubles = p.oP + (panel_global ? 0 : (long)TT_QR_PB * p.ldp);
     int nb = 8;
     while (nb > 1 && (p.oTaus + 2L * nb * Ls) * 8 > di.smem_optin - 1024) nb /= 2;
     p.nb = nb;
@@ -544,7 +553,7 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
     if (pl.smem_bytes > di.smem_optin)
         return fail(4, "linalg: %d x %d does not fit the kernel's shared memory (%ld B)", M, N, pl.smem_bytes);
     int G = 1;
-    if (nbatch == 1 && K >= g_coop_min_dim && K >= 2) {
+    if (nbatch == 1 && K >= g_coop_min_dim && K >= 2 && !panel_global) {
         const int nblk = (int)((K + nb - 1) / nb), npairs = (nblk + 1) / 2;
         G = imax(npairs, (int)((K + nw - 1) / nw));
         if (g_coop_min_dim <= 1) G = imax(G, 2);        // forced (tests): always exercise the multi-CTA path

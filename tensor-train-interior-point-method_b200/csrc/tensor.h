@@ -21,13 +21,35 @@ inline void check_rc(int rc, const char* what) {
     if (rc != 0) throw DriverError(rc, std::string(what) + ": " + ttipm_last_error());
 }
 
+// kernel categories of the per-launch profile (ttipm_amen_profile)
+enum ProfCat { CAT_MATVEC = 0, CAT_PHI, CAT_RHS, CAT_GEMM, CAT_QR, CAT_SVD, CAT_EWISE, CAT_DENSE, CAT_KRYLOV, CAT_COUNT };
+
+struct ProfRec {
+    int cat;
+    double work;                  // algorithmic flops (contractions, factorisations) or bytes (memory-bound helpers)
+    void* e0;                     // cudaEvent_t pair, created only while profiling
+    void* e1;
+};
+
 struct Ctx {
     tt_stream_t st = nullptr;
+    bool prof = false;            // time every launch with CUDA events (profiling passes only)
+    std::vector<ProfRec> recs;
     double* pinned = nullptr;     // host staging for scalar read-backs
     size_t pinned_cap = 0;
     long launches = 0;
     long syncs = 0;
     size_t bytes_live = 0, bytes_peak = 0;
+};
+
+// RAII bracket around the launches of one kernel category: a CUDA-event pair on the driver's stream while
+// Ctx::prof is set, nothing otherwise
+struct ProfScope {
+    Ctx& c;
+    bool on;
+    size_t idx = 0;
+    ProfScope(Ctx& ctx, int cat, double work);
+    ~ProfScope();
 };
 
 void* dev_alloc(Ctx& c, size_t bytes);

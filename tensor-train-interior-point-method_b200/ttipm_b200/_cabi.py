@@ -73,6 +73,7 @@ SIGNATURES = {
     "ttipm_amen_core_shape": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(i32)]),
     "ttipm_amen_get_core": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ttipm_amen_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "ttipm_amen_profile": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ttipm_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, i64, i64, i64, C.c_void_p, i64, i64,
                              i64, C.c_double, C.c_void_p, i64, i64, i64, C.c_int, C.c_void_p]),
 }

@@ -477,12 +477,20 @@ class NativeBlockAmen:
                                       "krylov_matvecs", "launches", "syncs", "peak_bytes", "trace_rows", "krylov_seconds",
                                       "krylov_flops"], stats.tolist()))
         self.stats.update(self.native_stats)
+        prof = np.zeros(27)
+        self._chk(self.lib.ttipm_amen_profile(self.h, prof.ctypes.data))
+        # per kernel category of a profiled run: (seconds, algorithmic flops | bytes, launches)
+        self.native_profile = {name: tuple(prof[3 * q:3 * q + 3]) for q, name in enumerate(PROFILE_CATEGORIES)}
         return out
 
     def solve(self, term_tol, r_max=100, eps=1e-12, nswp=22, x0=None, kick_rank=2, amen=True):
         st = self.prepare(x0, kick_rank, amen)
         _, res = self.run(st, term_tol, r_max, eps, nswp)
         return self.fetch(), res
+
+
+PROFILE_CATEGORIES = ("block_matvec", "phi_update", "rhs_contract", "bond_gemm", "qr", "svd", "memory_bound",
+                      "dense_schur", "krylov")
 
 
 def _cabi_i32():

@@ -260,6 +260,11 @@ class ReducedOperator:
 
 
 # ---- dense factorisations -------------------------------------------------------------------------
+def rt_error(rt, what):
+    from .runtime import TTIPMError
+    return TTIPMError(f"{what} failed: {rt.lib.ttipm_last_error().decode()}")
+
+
 def _mat3(A):
     return A if A.dim() == 3 else A.unsqueeze(0)
 
@@ -271,7 +276,10 @@ def qr(A, rt=None):
     nb, M, N = A3.shape
     Kk = min(M, N)
     Q, R = rt.empty(nb, M, Kk), rt.empty(nb, Kk, N)
-    ws = rt.empty(int(rt.lib.ttipm_qr_workspace(M, N, nb)))
+    nws = int(rt.lib.ttipm_qr_workspace(M, N, nb))
+    if nws <= 0:
+        raise rt_error(rt, f"ttipm_qr_workspace({M}, {N}, {nb})")
+    ws = rt.empty(nws)
     code = rt.lib.ttipm_qr(_ptr(A3), A3.stride(1), A3.stride(2), A3.stride(0) if nb > 1 else 0, M, N, _ptr(Q), _ptr(R),
                            _ptr(ws), nb, rt.stream())
     rt.check(code, "ttipm_qr")
@@ -285,7 +293,10 @@ def svd_left(A, rt=None):
     nb, M, N = A3.shape
     Kk = min(M, N)
     U, S, W = rt.empty(nb, M, Kk), rt.empty(nb, Kk), rt.empty(nb, Kk, N)
-    ws = rt.empty(int(rt.lib.ttipm_svd_workspace(M, N, nb)))
+    nws = int(rt.lib.ttipm_svd_workspace(M, N, nb))
+    if nws <= 0:
+        raise rt_error(rt, f"ttipm_svd_workspace({M}, {N}, {nb})")
+    ws = rt.empty(nws)
     code = rt.lib.ttipm_svd_left(_ptr(A3), A3.stride(1), A3.stride(2), A3.stride(0) if nb > 1 else 0, M, N, _ptr(U),
                                  _ptr(S), _ptr(W), _ptr(ws), C.c_void_p(0), nb, rt.stream())
     rt.check(code, "ttipm_svd_left")

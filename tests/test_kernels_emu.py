@@ -60,6 +60,11 @@ def test_qr_svd_cooperative(rt):
     KC.assert_small(KC.case_qr_svd(rt, shapes=((37, 23), (19, 40)), coop_min_dim=1, graded=True), tol=1e-12)
 
 
+def test_qr_svd_tall_panel_in_workspace(rt):
+    """unfoldings with more rows than a shared-memory reflector panel holds (> ~3500) keep the panel in the workspace"""
+    KC.assert_small(KC.case_qr_svd(rt, shapes=((4100, 5), (4, 3900))), tol=1e-12)
+
+
 def test_elementwise(rt):
     KC.assert_small(KC.case_elementwise(rt), tol=1e-13)
 

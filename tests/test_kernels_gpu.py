@@ -76,6 +76,11 @@ def test_qr_svd(rt):
                                                (88, 66), (220, 165), (165, 220), (40, 300))), tol=1e-11)
 
 
+def test_qr_svd_tall_panel_in_workspace(rt):
+    """unfoldings with more rows than a shared-memory reflector panel holds keep the panel in the workspace"""
+    KC.assert_small(KC.case_qr_svd(rt, shapes=((4100, 5), (4, 3900), (6000, 40))), tol=1e-11)
+
+
 def test_qr_svd_cooperative(rt):
     """multi-CTA panel QR + block Jacobi: forced onto small shapes, default dispatch at the AMEn truncation sizes
     (maxcut_13 rank 2: (4 R) x (3 r) up to ~440 x 330), graded spectra, > 512 rows (memory-resident reflector path)"""
