@@ -46,6 +46,7 @@ struct LinParams {
     int M1, N1;          // first QR: M x N (tall, square, QR mode) or N x M (wide SVD, factors A^T)
     int Mj;              // accumulator row length
     int nb;              // Jacobi block rows
+    int resident;        // single CTA with every row [R | accumulator] in shared memory
     int ldp;             // panel leading dimension in shared memory
     int oOrd, oSvS, oTaus, oP;   // shared-memory offsets (doubles)
     int nbatch;
@@ -84,17 +85,20 @@ TT_DEV double lin_rsqrt(double x) { return 1.0 / sqrt(x); }
 // x <- (I - tj v v^T) x for a vector held in registers with the fixed mapping element i <-> (lane, q = i / 32);
 // v[j] = 1 implicit, v[i] given for j < i < len (v may point before its first valid element), zero above j
 TT_DEV void lin_reflect_reg(double (&reg)[TT_LIN_REG], const double* v, int j, int len, double tj, int lane) {
-    double vv[TT_LIN_REG];
     double d = 0.0;
 #pragma unroll
     for (int q = 0; q < TT_LIN_REG; ++q) {
         const int i = lane + 32 * q;
-        vv[q] = (i > j && i < len) ? v[i] : (i == j ? 1.0 : 0.0);
-        d += vv[q] * reg[q];
+        const double vv = (i > j && i < len) ? v[i] : (i == j ? 1.0 : 0.0);
+        d += vv * reg[q];
     }
     d = warp_sum(d) * tj;
 #pragma unroll
-    for (int q = 0; q < TT_LIN_REG; ++q) reg[q] -= d * vv[q];
+    for (int q = 0; q < TT_LIN_REG; ++q) {
+        const int i = lane + 32 * q;
+        const double vv = (i > j && i < len) ? v[i] : (i == j ? 1.0 : 0.0);
+        reg[q] -= d * vv;
+    }
 }
 // same for a vector in memory (len > 32 * TT_LIN_REG); element i at x[i * xs]; a thread only re-reads its own writes
 TT_DEV void lin_reflect_mem(double* x, long xs, const double* v, int j, int len, double tj, int lane) {
@@ -263,24 +267,36 @@ TT_DEV void lin_apply_q(LinCtx& c, const double* W, const double* tau, int Mq, i
 // orthogonalise two rows held in shared memory: [row of R (K) | accumulator row (Mj)], total length Ls
 TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, int lane) {
     double saa = 0.0, sbb = 0.0, sab = 0.0;
+#pragma unroll 4
     for (int i = lane; i < K; i += 32) {
         const double x = ra[i], y = rb[i];
         saa += x * x;
         sbb += y * y;
         sab += x * y;
     }
+#ifndef TTIPM_EMU
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {           // three interleaved butterflies
+        saa += __shfl_xor_sync(0xffffffffu, saa, o);
+        sbb += __shfl_xor_sync(0xffffffffu, sbb, o);
+        sab += __shfl_xor_sync(0xffffffffu, sab, o);
+    }
+#else
     saa = warp_sum(saa);
     sbb = warp_sum(sbb);
     sab = warp_sum(sab);
+#endif
     if (!(sab * sab > tol2 * saa * sbb)) return false;
     // tan of the rotation angle: zeta = (sbb - saa) / (2 sab), tg = sign(zeta) / (|zeta| + sqrt(1 + zeta^2))
     const double d = sbb - saa;
     const double tg = 2.0 * sab / (d + copysign(sqrt(d * d + 4.0 * sab * sab), d));
     const double cs = lin_rsqrt(1.0 + tg * tg), sn = cs * tg;
+    const double c1 = cs, s1 = -sn, c2 = sn, s2 = cs;
+#pragma unroll 4
     for (int i = lane; i < Ls; i += 32) {
         const double x = ra[i], y = rb[i];
-        ra[i] = cs * x - sn * y;
-        rb[i] = sn * x + cs * y;
+        ra[i] = c1 * x + s1 * y;
+        rb[i] = c2 * x + s2 * y;
     }
     return true;
 }
@@ -318,7 +334,9 @@ TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flag
                     if (q >= cnt) continue;
                     const long row = (long)blk * nb + q;
                     double* dstr = rowsS + (long)slot * Ls;
+#pragma unroll 8
                     for (int i = lane; i < K; i += 32) dstr[i] = ld_cg(G + row * K + i);
+#pragma unroll 8
                     for (int i = lane; i < Mj; i += 32) dstr[K + i] = ld_cg(Jt + row * Mj + i);
                 }
                 __syncthreads();
@@ -387,8 +405,61 @@ TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flag
     return sweeps;
 }
 
+// Single-CTA variant for unfoldings whose rows [R | accumulator] fit in shared memory (K * (K + Mj) doubles): every
+// row stays resident for the whole iteration, each warp owns one row pair of a round-robin step, and a step costs one
+// block barrier.  G, Jt are read once and written once.
+TT_DEV int lin_jacobi_resident(LinCtx& c, double* G, double* Jt, int K, int Mj) {
+    const int Ls = K + Mj, lane = c.lane, wid = c.wid, nw = c.nw;
+    const int Ke = K + (K & 1), half = Ke / 2;
+    const double tol = 2.220446049250313e-16 * sqrt((double)K), tol2 = tol * tol;
+    int* rotated = (int*)(c.smem + 36);
+    double* rowsS = c.smem + c.p.oTaus;
+    if (K < 2) return 0;
+    __syncthreads();
+    for (int row = wid; row < K; row += nw) {
+        double* dstr = rowsS + (long)row * Ls;
+        for (int i = lane; i < K; i += 32) dstr[i] = ld_cg(G + (long)row * K + i);
+        for (int i = lane; i < Mj; i += 32) dstr[K + i] = ld_cg(Jt + (long)row * Mj + i);
+    }
+    int sweeps = 0;
+    for (; sweeps < 60;) {
+        __syncthreads();
+        if (threadIdx.x == 0) *rotated = 0;
+        __syncthreads();
+        bool rot = false;
+        for (int u = 0; u < Ke - 1; ++u) {
+            for (int q = wid; q < half; q += nw) {
+                int x, y;
+                if (q == 0) {
+                    x = Ke - 1;
+                    y = u;
+                } else {
+                    x = (u + q) % (Ke - 1);
+                    y = (u - q + Ke - 1) % (Ke - 1);
+                }
+                if (x >= K || y >= K) continue;
+                if (x > y) { const int z = x; x = y; y = z; }
+                rot |= lin_jacobi_pair(rowsS + (long)x * Ls, rowsS + (long)y * Ls, K, Ls, tol2, lane);
+            }
+            __syncthreads();
+        }
+        if (rot && lane == 0) *rotated = 1;
+        __syncthreads();
+        ++sweeps;
+        if (*rotated == 0) break;
+    }
+    for (int row = wid; row < K; row += nw) {
+        const double* srcr = rowsS + (long)row * Ls;
+        for (int i = lane; i < K; i += 32) G[(long)row * K + i] = srcr[i];
+        for (int i = lane; i < Mj; i += 32) Jt[(long)row * Mj + i] = srcr[K + i];
+    }
+    c.sync();
+    return sweeps;
+}
+
 // grid = (CTAs per matrix, batch)
-TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_linalg(const LinParams p) {
+template <int NT>
+TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
     TT_SMEM_DECL(smem_raw);
     double* smem = (double*)smem_raw;
     const int batch = blockIdx.y;
@@ -452,7 +523,7 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_linalg(const LinParams p) {
     lin_apply_q(c, Wq, tq, Mq, K, K, 0, nullptr, nullptr, Jt, Mj, 1);          // rows of Q^T (K x Mq), Mj == Mq
     c.sync();
     const long long t_q = lin_now();
-    const int sweeps = lin_jacobi(c, G, Jt, K, Mj, flags, tm);
+    const int sweeps = p.resident ? lin_jacobi_resident(c, G, Jt, K, Mj) : lin_jacobi(c, G, Jt, K, Mj, flags, tm);
     const long long t_jac = lin_now();
     // singular values = row norms
     for (int i = c.gw; i < K; i += c.GW) {
@@ -504,10 +575,12 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_linalg(const LinParams p) {
 }
 
 static int g_coop_min_dim = 17;
+static int g_resident_max_dim = 32;
 
 struct LinPlan {
     LinParams p;
     int grid;
+    int threads;
     long smem_bytes;
     long ws_total;
 };
@@ -530,7 +603,15 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
     p.oJt = o; o += mode == 0 ? K * p.Mj : 0;
     p.oSv = o; o += K;
     DevInfo di = dev_info();
-    const int nw = block_threads() / 32;
+    // 256-thread CTAs (8 warps = the 8 concurrent row pairs of a block-pair step; measured on B200: the pairwise
+    // rotations are bound by shared-memory bandwidth, 16 warps per CTA do not finish a step sooner); the resident
+    // single-CTA variant runs 512 threads above 16 rows
+#ifdef TTIPM_EMU
+    pl.threads = block_threads();
+#else
+    pl.threads = 256;
+#endif
+    const int nw = pl.threads / 32;
     p.ldp = p.M1 + (p.M1 & 1);
     // a panel of TT_QR_PB columns of M1 rows normally sits in shared memory; columns too long for that keep the
     // panel in the workspace and the matrix is factored by one CTA (rare: unfoldings with > ~3000 rows)
@@ -548,18 +629,29 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
     int nb = 8;
     while (nb > 1 && (p.oTaus + 2L * nb * Ls) * 8 > di.smem_optin - 1024) nb /= 2;
     p.nb = nb;
-    const long jac_doubles = mode == 0 ? p.oTaus + 2L * nb * Ls : 0;
+    long jac_doubles = mode == 0 ? p.oTaus + 2L * nb * Ls : 0;
+    // every row resident in one CTA's shared memory when it fits (forced multi-CTA runs of the tests excepted)
+    // (measured on B200: one SM's issue slots bound the resident variant, so beyond K ~ 32 a single matrix is faster
+    // spread over several CTAs; batched calls keep one CTA per matrix)
+    p.resident = (mode == 0 && K >= 2 && (p.oTaus + K * Ls) * 8 <= di.smem_optin - 1024 &&
+                  (nbatch > 1 || K <= g_resident_max_dim) && !(nbatch == 1 && g_coop_min_dim <= 1)) ? 1 : 0;
+    if (p.resident) jac_doubles = p.oTaus + K * Ls;
     pl.smem_bytes = 8 * (qr_doubles > jac_doubles ? qr_doubles : jac_doubles);
     if (pl.smem_bytes > di.smem_optin)
         return fail(4, "linalg: %d x %d does not fit the kernel's shared memory (%ld B)", M, N, pl.smem_bytes);
     int G = 1;
-    if (nbatch == 1 && K >= g_coop_min_dim && K >= 2 && !panel_global) {
+    if (nbatch == 1 && K >= g_coop_min_dim && K >= 2 && !panel_global && !p.resident) {
         const int nblk = (int)((K + nb - 1) / nb), npairs = (nblk + 1) / 2;
-        G = imax(npairs, (int)((K + nw - 1) / nw));
+        G = imax(npairs, (int)((K + 7) / 8));          // Jacobi keeps npairs CTAs busy, the QR phases one warp per column
         if (g_coop_min_dim <= 1) G = imax(G, 2);        // forced (tests): always exercise the multi-CTA path
         G = imax(1, imin(G, imin(64, di.sms)));
     }
     pl.grid = G;
+#ifdef TTIPM_EMU
+    if (p.resident && K > 16) pl.threads = 2 * block_threads();
+#else
+    if (p.resident && K > 16) pl.threads = 512;
+#endif
     return 0;
 }
 
@@ -578,16 +670,18 @@ static int lin_launch(int mode, const double* A, long a_rs, long a_cs, long a_bs
         DevInfo di = dev_info();
         static int optin_done = 0;
         if (!optin_done) {
-            cudaFuncSetAttribute((const void*)k_linalg, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
+            cudaFuncSetAttribute((const void*)k_linalg<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
             optin_done = 1;
         }
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linalg, block_threads(), (size_t)pl.smem_bytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linalg<512>, pl.threads, (size_t)pl.smem_bytes);
         if (per_sm < 1) return fail(4, "linalg: kernel does not fit on an SM with %ld B shared memory", pl.smem_bytes);
         if (G > per_sm * di.sms) G = per_sm * di.sms;
     }
 #endif
-    return launch_kernel("k_linalg", k_linalg, dim3(G, nbatch), dim3(block_threads()), (size_t)pl.smem_bytes, st, G > 1, p);
+    if (G > 1)
+        return launch_kernel("k_linalg", k_linalg<512>, dim3(G, nbatch), dim3(pl.threads), (size_t)pl.smem_bytes, st, true, p);
+    return launch_kernel("k_linalg", k_linalg<512>, dim3(1, nbatch), dim3(pl.threads), (size_t)pl.smem_bytes, st, false, p);
 }
 
 }  // namespace ttipm

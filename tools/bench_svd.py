@@ -58,7 +58,8 @@ def run(rt, a, coop, iters=5):
 def main():
     rt = get_runtime()
     rng = np.random.default_rng(0)
-    shapes = [(88, 66), (220, 165), (165, 220), (440, 330), (330, 440), (408, 300), (24, 440)]
+    shapes = [(16, 12), (32, 24), (64, 48), (88, 66), (136, 81), (296, 102), (102, 296), (220, 165), (165, 220), (440, 330),
+              (330, 440), (24, 440)]
     if len(sys.argv) > 1:
         shapes = [tuple(int(v) for v in s.split("x")) for s in sys.argv[1:]]
     out = []
