@@ -57,6 +57,18 @@ int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, int L, int r,
                        int64_t y_mode_stride, int64_t y_batch_stride, double y_scale, const double* sub,
                        double sub_scale, double* sumsq, int nbatch, void* stream);
 
+/* Local blocks whose chain costs at least this many flops per call run as three grouped contraction-GEMM launches
+ * (128x128 / 64x64 DMMA tiles over the whole machine, intermediates in L2-resident scratch from the stream-ordered
+ * allocator) instead of the fused one-CTA-per-slab kernel.  Returns the previous threshold (default 2e8);
+ * a negative argument only queries. */
+double ttipm_matvec_big_min_flops(double min_flops);
+/* Test hook of the grouped-GEMM path: force this split-K factor wherever K allows (0 = automatic: split only when the
+ * output tiles alone cannot fill the machine).  Returns the previous value; a negative argument only queries. */
+int ttipm_cgemm_force_ksplit(int ksplit);
+/* Tuning hook: force the tile shape of the grouped-GEMM launches (0 = 128x128, 1 = 128x64, 2 = 64x64, -1 = automatic).
+ * Returns the previous value; an argument below -1 only queries. */
+int ttipm_cgemm_force_cfg(int cfg);
+
 /* K4 -- diag[l,m,L] = sum_s,S P1[l,s,l] A[s,m,m,S] P2[L,S,L]   (reference src/tt_ipm.py:191, :292);
  * if invert != 0 stores 1/diag (the inv_I of the Schur reduction). */
 int ttipm_local_diag(const ttipm_term* term, int l, int L, int nmode, int invert, double* out, void* stream);

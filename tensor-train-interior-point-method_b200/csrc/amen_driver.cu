@@ -1140,21 +1140,7 @@ struct ttipm_amen {
     }
 
 extern "C" ttipm_amen* ttipm_amen_create(int d, int block_size, int ineq, void* stream) {
-#ifndef TTIPM_EMU
-    {   // keep freed blocks in the stream-ordered pool across synchronisations (the default trims it to zero)
-        static bool pool_ready = false;
-        if (!pool_ready) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                unsigned long long keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            pool_ready = true;
-        }
-    }
-#endif
+    pool_keep_freed_blocks();
     ttipm_amen* h = new ttipm_amen();
     h->a.c.st = (tt_stream_t)stream;
     h->a.d = d;

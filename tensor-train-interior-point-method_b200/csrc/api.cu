@@ -42,6 +42,23 @@ int check_launch(const char* what) {
     return 0;
 }
 
+// keep freed blocks in the stream-ordered pool across synchronisations (the default trims it to zero, which turns every
+// scratch allocation after a sync into a fresh cudaMalloc)
+void pool_keep_freed_blocks() {
+#ifndef TTIPM_EMU
+    static bool pool_ready = false;
+    if (pool_ready) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_ready = true;
+#endif
+}
+
 DevInfo dev_info() {
     static DevInfo cached = {0, 0};
     if (cached.sms) return cached;

@@ -2,6 +2,8 @@
 #pragma once
 #include <limits.h>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <vector>
 #include "../../include/ttipm.h"
 #include "common.cuh"
 #include "matvec.cuh"
@@ -13,6 +15,7 @@ struct DevInfo {
     int smem_optin;
 };
 DevInfo dev_info();
+void pool_keep_freed_blocks();
 int block_threads();
 int dev_memset(void* p, int v, size_t bytes, tt_stream_t st);
 int dev_copy(void* dst, const void* src, size_t bytes, tt_stream_t st);
@@ -34,5 +37,11 @@ static inline int convert_term(const ttipm_term& in, MvTerm& out) {
     out.s = in.s; out.S = in.S; out.in_blk = in.in_block; out.out_blk = in.out_block; out.alpha = in.alpha;
     return 0;
 }
+
+// large-rank path of K1 (cgemm.cu)
+bool mv_big_wanted(const MvTerm* t, int nterms, int l, int L, int r, int R, int nm, int nb_out, int nbatch);
+int mv_big(const MvTerm* t, int nterms, int l, int L, int r, int R, int nm, int nb_out, const double* x, long x_bs,
+           long x_rs, long x_ns, long x_batch, double* y, long y_bs, long y_rs, long y_ns, long y_batch, double y_scale,
+           const double* sub, double sub_scale, double* sumsq, int nbatch, tt_stream_t st);
 
 }  // namespace ttipm

@@ -59,7 +59,7 @@ TT_DEV int axoff(const AxisMap& a, int i) { return (i / a.n1) * a.s0 + (i % a.n1
 // ---------------------------------------------------------------------------
 #ifndef TTIPM_EMU
 TT_DEV void dmma884(double a, double b, double& c0, double& c1) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
@@ -203,6 +203,28 @@ TT_DEV void tgemm(int M, int N, int K, const double* __restrict__ A, AxisMap aM,
     else
         tgemm_tiles<1, 1>(M, N, K, A, B, oAM, oAK, oBK, oBN, store);
     __syncthreads();
+}
+
+// One row of a memory-bound copy kernel: dst[j] = op(src[j]) for j = tx, tx + tw, ... < n, eight independent loads
+// in flight per thread before the first store (dst and src never alias; src == nullptr writes zeros).
+// op: 0 copy, 1 multiply by s, 2 divide by s.
+TT_DEV void row_stream(double* __restrict__ dst, const double* __restrict__ src, int n, int tx, int tw, int op, double s) {
+    if (!src) {
+        for (int j = tx; j < n; j += tw) dst[j] = 0.0;
+        return;
+    }
+    int j = tx;
+    for (; j + 7 * tw < n; j += 8 * tw) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = src[j + u * tw];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dst[j + u * tw] = op == 0 ? v[u] : (op == 1 ? v[u] * s : v[u] / s);
+    }
+    for (; j < n; j += tw) {
+        const double v = src[j];
+        dst[j] = op == 0 ? v : (op == 1 ? v * s : v / s);
+    }
 }
 
 TT_HD int align_up(int v, int a) { return (v + a - 1) / a * a; }

@@ -15,8 +15,32 @@ struct PermParams {
     const double* scale;
     int axis, mode;   // mode 0 none, 1 multiply, 2 divide by scale[o_axis]
     long total;
+    int tw, tw_shift; // > 0: row-tiled variant (last axis in place), tw = threads along the last axis (power of two)
 };
 TT_GLOBAL void k_permute4(const PermParams p) {
+    if (p.tw > 0) {
+        // last axis contiguous on both sides (every permutation of the sweep): tw threads run along it, the
+        // remaining threads of the CTA take further rows; one index decode per row, independent loads in flight
+        const int tx = threadIdx.x & (p.tw - 1), ty = threadIdx.x >> p.tw_shift, rows_per = blockDim.x >> p.tw_shift;
+        const long rows = (long)p.od[0] * p.od[1] * p.od[2];
+        const int inner = p.od[3];
+        for (long row = (long)blockIdx.x * rows_per + ty; row < rows; row += (long)gridDim.x * rows_per) {
+            long t = row;
+            const int o2 = (int)(t % p.od[2]); t /= p.od[2];
+            const int o1 = (int)(t % p.od[1]); t /= p.od[1];
+            const int o0 = (int)t;
+            const double* src = p.in + o0 * p.is_[0] + o1 * p.is_[1] + o2 * p.is_[2];
+            double* dst = p.out + row * inner;
+            if (p.mode && p.axis == 3) {
+                for (int j = tx; j < inner; j += p.tw) dst[j] = p.mode == 1 ? src[j] * p.scale[j] : src[j] / p.scale[j];
+            } else {
+                // (a division stays a division: same rounding as the reference's `/ scales`)
+                const double sv = p.mode ? p.scale[p.axis == 0 ? o0 : p.axis == 1 ? o1 : o2] : 1.0;
+                row_stream(dst, src, inner, tx, p.tw, p.mode, sv);
+            }
+        }
+        return;
+    }
     const long stride = (long)gridDim.x * blockDim.x;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += stride) {
         long t = i;
@@ -65,21 +89,50 @@ struct EwParams {
     long a_rs, b_rs, c_rs, w_rs, o_rs;
     double* out;
     double* sumsq;
+    int tw, tw_shift;
 };
 // out = w .* (alpha a + beta b) + gamma c   over a (rows x inner) panel set; optional sum of squares
+TT_DEV double ew_value(const EwParams& p, long ia, long ib, long ic, long iw) {
+    double v = p.alpha * p.a[ia];
+    if (p.b) v += p.beta * p.b[ib];
+    if (p.w) v *= p.w[iw];
+    if (p.c) v += p.gamma * p.c[ic];
+    return v;
+}
 TT_GLOBAL void k_ewise(const EwParams p) {
     TT_SMEM_DECL(smem_raw);
     double* scr = (double*)smem_raw;
-    const long tot = (long)p.rows * p.inner, stride = (long)gridDim.x * blockDim.x;
     double ss = 0.0;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += stride) {
-        const long row = i / p.inner, q = i % p.inner;
-        double v = p.alpha * p.a[row * p.a_rs + q];
-        if (p.b) v += p.beta * p.b[row * p.b_rs + q];
-        if (p.w) v *= p.w[row * p.w_rs + q];
-        if (p.c) v += p.gamma * p.c[row * p.c_rs + q];
-        if (p.out) p.out[row * p.o_rs + q] = v;
-        ss += v * v;
+    if (p.rows == 1) {
+        // contiguous operands: flat grid-stride loop, eight independent elements per thread and trip
+        const long tot = p.inner, stride = (long)gridDim.x * blockDim.x;
+        long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 7 * stride < tot; i += 8 * stride) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = ew_value(p, i + u * stride, i + u * stride, i + u * stride, i + u * stride);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (p.out) p.out[i + u * stride] = v[u];
+                ss += v[u] * v[u];
+            }
+        }
+        for (; i < tot; i += stride) {
+            const double v = ew_value(p, i, i, i, i);
+            if (p.out) p.out[i] = v;
+            ss += v * v;
+        }
+    } else {
+        // strided panels (x[:, j] slices): tw threads along a row, the rest of the CTA on further rows
+        const int tx = threadIdx.x & (p.tw - 1), ty = threadIdx.x >> p.tw_shift, rows_per = blockDim.x >> p.tw_shift;
+        for (long row = (long)blockIdx.x * rows_per + ty; row < p.rows; row += (long)gridDim.x * rows_per) {
+#pragma unroll 4
+            for (int q = tx; q < p.inner; q += p.tw) {
+                const double v = ew_value(p, row * p.a_rs + q, row * p.b_rs + q, row * p.c_rs + q, row * p.w_rs + q);
+                if (p.out) p.out[row * p.o_rs + q] = v;
+                ss += v * v;
+            }
+        }
     }
     if (p.sumsq) {
         ss = block_sum(ss, scr);
@@ -128,6 +181,12 @@ TT_GLOBAL void k_trunc_resnorms(const TruncParams p) {
 
 using namespace ttipm;
 
+// threads along a row of `inner` elements: the smallest power of two >= min(inner, block) (at least 1)
+static void row_tile(int inner, int block, int& tw, int& shift) {
+    tw = 1; shift = 0;
+    while (tw < inner && tw < block) { tw <<= 1; ++shift; }
+}
+
 extern "C" int ttipm_permute4(const double* in, const int32_t* in_dims, const int32_t* perm, double* out,
                               const double* scale, int scale_axis, int scale_mode, void* stream) {
     PermParams p;
@@ -148,6 +207,12 @@ extern "C" int ttipm_permute4(const double* in, const int32_t* in_dims, const in
     p.in = in; p.out = out; p.scale = scale; p.axis = scale_axis; p.mode = scale ? scale_mode : 0;
     const int bt = block_threads();
     long blocks = (p.total + bt - 1) / bt;
+    p.tw = 0; p.tw_shift = 0;
+    if (perm[3] == 3) {
+        row_tile(p.od[3], bt, p.tw, p.tw_shift);
+        const long rows = p.total / p.od[3], rows_per = bt >> p.tw_shift;
+        blocks = (rows + rows_per - 1) / rows_per;
+    }
     const long cap = (long)dev_info().sms * 8;
     if (blocks > cap) blocks = cap;
     return launch_kernel("k_permute4", k_permute4, dim3((unsigned)blocks), dim3(bt), 0, (tt_stream_t)stream, false, p);
@@ -169,7 +234,17 @@ extern "C" int ttipm_ewise(int rows, int inner, double alpha, const double* a, i
     p.out = out; p.o_rs = out_rs; p.sumsq = sumsq;
     const int bt = block_threads();
     long blocks = ((long)rows * inner + bt - 1) / bt;
-    if (blocks > EW_MAX_PARTS) blocks = EW_MAX_PARTS;
+    row_tile(inner, bt, p.tw, p.tw_shift);
+    if (rows > 1) {
+        const long rows_per = bt >> p.tw_shift;
+        blocks = (rows + rows_per - 1) / rows_per;
+    } else {
+        blocks = (blocks + 7) / 8;                   // eight elements per thread and trip
+    }
+    // the sum-of-squares partials have EW_MAX_PARTS slots; without them fill the machine
+    const long cap = sumsq ? EW_MAX_PARTS : (long)dev_info().sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
     tt_stream_t st = (tt_stream_t)stream;
     if (sumsq && dev_memset(sumsq, 0, sizeof(double) * EW_MAX_PARTS, st)) return fail(5, "ewise: memset failed");
     return launch_kernel("k_ewise", k_ewise, dim3((unsigned)blocks), dim3(bt), 40 * 8, st, false, p);

@@ -132,6 +132,15 @@ extern "C" int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, in
         if (terms[i].S > Smax) Smax = terms[i].S;
     }
     p.nterms = nterms;
+    if (!fits_int(x_row_stride) || !fits_int(x_mode_stride) || !fits_int(y_row_stride) || !fits_int(y_mode_stride))
+        return fail(1, "block_matvec: x / y strides too large");
+    if (sumsq && dev_memset(sumsq, 0, sizeof(double) * (size_t)nbatch * nb_out * L, (tt_stream_t)stream))
+        return fail(5, "memset failed");
+    // large local blocks: every stage of the chain is a machine-filling GEMM (cgemm.cu)
+    if (mv_big_wanted(p.t, nterms, l, L, r, R, nmode, nb_out, nbatch))
+        return mv_big(p.t, nterms, l, L, r, R, nmode, nb_out, x, x_block_stride, x_row_stride, x_mode_stride, x_batch_stride,
+                      y, y_block_stride, y_row_stride, y_mode_stride, y_batch_stride, y_scale, sub, sub_scale, sumsq, nbatch,
+                      (tt_stream_t)stream);
     DevInfo di = dev_info();
     if (mv_plan(p.g, l, L, r, R, nmode, smax, Smax, nb_out, (di.sms * 2 + nbatch - 1) / nbatch, di.smem_optin))
         return fail(4, "block_matvec: shape l=%d L=%d r=%d R=%d s=%d S=%d needs %d B shared memory (> %d)", l, L, r,
@@ -139,10 +148,8 @@ extern "C" int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, in
     p.x = x; p.x_bs = x_block_stride; p.x_rs = x_row_stride; p.x_ns = x_mode_stride; p.x_batch = x_batch_stride;
     p.y = y; p.y_bs = y_block_stride; p.y_rs = y_row_stride; p.y_ns = y_mode_stride; p.y_batch = y_batch_stride;
     p.y_scale = y_scale; p.sub_scale = sub_scale;
-    if (!fits_int(x_row_stride) || !fits_int(x_mode_stride)) return fail(1, "block_matvec: x strides too large");
     p.sub = sub; p.sumsq = sumsq; p.nb_out = nb_out;
     tt_stream_t st = (tt_stream_t)stream;
-    if (sumsq && dev_memset(sumsq, 0, sizeof(double) * (size_t)nbatch * nb_out * L, st)) return fail(5, "memset failed");
     return launch_kernel("k_block_matvec", k_block_matvec, dim3(nb_out * p.g.ntiles, nbatch), dim3(block_threads()),
                          p.g.smem_bytes, st, false, p);
 }

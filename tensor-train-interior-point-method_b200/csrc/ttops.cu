@@ -10,27 +10,36 @@ struct BdParams {
     double* out;
     int ra, Ra, rb, Rb, n, mode;   // mode 0 first (concat last axis), 1 middle (block diagonal), 2 last (concat first axis)
     long total;
+    int tw, tw_shift;              // threads along the rank axis (power of two)
 };
 // reference cy_src/tt_ops_cy.pyx:229-258
 TT_GLOBAL void k_block_diag(const BdParams p) {
-    const int ro = p.mode == 0 ? p.ra : p.ra + p.rb;
+    // rows = (i, q) of the output core, tw threads along the rank axis j; one decode per row, coalesced segments
     const int Ro = p.mode == 2 ? p.Ra : p.Ra + p.Rb;
-    (void)ro;
-    const long stride = (long)gridDim.x * blockDim.x;
-    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < p.total; e += stride) {
-        const int j = (int)(e % Ro);
-        const int q = (int)((e / Ro) % p.n);
-        const int i = (int)(e / ((long)Ro * p.n));
-        double v = 0.0;
+    const int ro = p.mode == 0 ? p.ra : p.ra + p.rb;
+    const int tx = threadIdx.x & (p.tw - 1), ty = threadIdx.x >> p.tw_shift, rows_per = blockDim.x >> p.tw_shift;
+    const long rows = (long)ro * p.n;
+    for (long row = (long)blockIdx.x * rows_per + ty; row < rows; row += (long)gridDim.x * rows_per) {
+        const int i = (int)(row / p.n), q = (int)(row % p.n);
+        double* dst = p.out + row * Ro;
+        // source segments of this output row: [0, Ra) from a (or zero), [Ra, Ra + Rb) from b (or zero)
+        const double* sa = nullptr;
+        const double* sb = nullptr;
         if (p.mode == 0) {
-            v = j < p.Ra ? p.a[((long)i * p.n + q) * p.Ra + j] : p.b[((long)i * p.n + q) * p.Rb + j - p.Ra];
+            sa = p.a + ((long)i * p.n + q) * p.Ra;
+            sb = p.b + ((long)i * p.n + q) * p.Rb;
         } else if (p.mode == 2) {
-            v = i < p.ra ? p.a[((long)i * p.n + q) * p.Ra + j] : p.b[((long)(i - p.ra) * p.n + q) * p.Rb + j];
+            sa = i < p.ra ? p.a + ((long)i * p.n + q) * p.Ra : p.b + ((long)(i - p.ra) * p.n + q) * p.Rb;
         } else {
-            if (i < p.ra && j < p.Ra) v = p.a[((long)i * p.n + q) * p.Ra + j];
-            else if (i >= p.ra && j >= p.Ra) v = p.b[((long)(i - p.ra) * p.n + q) * p.Rb + j - p.Ra];
+            if (i < p.ra) sa = p.a + ((long)i * p.n + q) * p.Ra;
+            else sb = p.b + ((long)(i - p.ra) * p.n + q) * p.Rb;
         }
-        p.out[e] = v;
+        if (p.mode == 2) {
+            row_stream(dst, sa, Ro, tx, p.tw, 0, 1.0);
+        } else {
+            row_stream(dst, sa, p.Ra, tx, p.tw, 0, 1.0);
+            row_stream(dst + p.Ra, sb, p.Rb, tx, p.tw, 0, 1.0);
+        }
     }
 }
 
@@ -39,28 +48,28 @@ struct EmbedParams {
     double* out;
     int r, R, q, mode;   // mode 0: I (x) M, 1: M (x) I  (in (r,2,2,R) -> out (r,4,4,R));  2: diag (in (r,q,R) -> out (r,q,q,R))
     long total;
+    int tw, tw_shift;
 };
 // reference src/tt_ops.py:360-375, :312-316
 TT_GLOBAL void k_embed(const EmbedParams p) {
-    const long stride = (long)gridDim.x * blockDim.x;
     const int Q = p.mode == 2 ? p.q : 4;
-    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < p.total; e += stride) {
-        const int Rr = (int)(e % p.R);
-        const int col = (int)((e / p.R) % Q);
-        const int row = (int)((e / ((long)p.R * Q)) % Q);
-        const int rr = (int)(e / ((long)p.R * Q * Q));
-        double v = 0.0;
+    const int tx = threadIdx.x & (p.tw - 1), ty = threadIdx.x >> p.tw_shift, rows_per = blockDim.x >> p.tw_shift;
+    const long rows = (long)p.r * Q * Q;
+    for (long rw = (long)blockIdx.x * rows_per + ty; rw < rows; rw += (long)gridDim.x * rows_per) {
+        const int col = (int)(rw % Q), row = (int)((rw / Q) % Q), rr = (int)(rw / ((long)Q * Q));
+        const double* src = nullptr;            // the input row this output row copies, or none (zeros)
         if (p.mode == 2) {
-            if (row == col) v = p.in[((long)rr * Q + row) * p.R + Rr];
+            if (row == col) src = p.in + ((long)rr * Q + row) * p.R;
         } else {
             const int m = row >> 1, i = row & 1, n = col >> 1, j = col & 1;
             if (p.mode == 0) {
-                if (m == n) v = p.in[(((long)rr * 2 + i) * 2 + j) * p.R + Rr];
+                if (m == n) src = p.in + (((long)rr * 2 + i) * 2 + j) * p.R;
             } else {
-                if (i == j) v = p.in[(((long)rr * 2 + m) * 2 + n) * p.R + Rr];
+                if (i == j) src = p.in + (((long)rr * 2 + m) * 2 + n) * p.R;
             }
         }
-        p.out[e] = v;
+        double* dst = p.out + rw * p.R;
+        row_stream(dst, src, p.R, tx, p.tw, 0, 1.0);
     }
 }
 
@@ -83,6 +92,20 @@ TT_GLOBAL void k_scale2d(const Scale2Params p) {
     }
 }
 
+static void row_tile2(int inner, int block, int& tw, int& shift) {
+    tw = 1; shift = 0;
+    while (tw < inner && tw < block) { tw <<= 1; ++shift; }
+}
+// grid of the row-tiled kernels: rows / (rows per CTA pass), capped at 8 CTAs per SM
+static unsigned grid_rows(long rows, int shift) {
+    const long rows_per = block_threads() >> shift;
+    long blocks = (rows + rows_per - 1) / rows_per;
+    const long cap = (long)dev_info().sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
 static unsigned grid_for(long total) {
     const int bt = block_threads();
     long blocks = (total + bt - 1) / bt;
@@ -100,20 +123,22 @@ extern "C" int ttipm_block_diag(const double* a, const double* b, double* out, i
                                 int mode, void* stream) {
     if (mode < 0 || mode > 2) return fail(1, "block_diag: mode %d", mode);
     if ((mode == 0 && ra != rb) || (mode == 2 && Ra != Rb)) return fail(1, "block_diag: boundary ranks differ");
-    BdParams p{a, b, out, ra, Ra, rb, Rb, n, mode, 0};
+    BdParams p{a, b, out, ra, Ra, rb, Rb, n, mode, 0, 1, 0};
     const long ro = mode == 0 ? ra : ra + rb, Ro = mode == 2 ? Ra : Ra + Rb;
     p.total = ro * n * Ro;
-    return launch_kernel("k_block_diag", k_block_diag, dim3(grid_for(p.total)), dim3(block_threads()), 0,
+    row_tile2((int)Ro, block_threads(), p.tw, p.tw_shift);
+    return launch_kernel("k_block_diag", k_block_diag, dim3(grid_rows(ro * n, p.tw_shift)), dim3(block_threads()), 0,
                          (tt_stream_t)stream, false, p);
 }
 
 extern "C" int ttipm_embed(const double* in, double* out, int r, int R, int q, int mode, void* stream) {
     if (mode < 0 || mode > 2) return fail(1, "embed: mode %d", mode);
-    EmbedParams p{in, out, r, R, q, mode, 0};
+    EmbedParams p{in, out, r, R, q, mode, 0, 1, 0};
     const long Q = mode == 2 ? q : 4;
     p.total = (long)r * Q * Q * R;
-    return launch_kernel("k_embed", k_embed, dim3(grid_for(p.total)), dim3(block_threads()), 0, (tt_stream_t)stream,
-                         false, p);
+    row_tile2(R, block_threads(), p.tw, p.tw_shift);
+    return launch_kernel("k_embed", k_embed, dim3(grid_rows((long)r * Q * Q, p.tw_shift)), dim3(block_threads()), 0,
+                         (tt_stream_t)stream, false, p);
 }
 
 extern "C" int ttipm_scale2d(const double* in, int64_t in_rs, int64_t in_cs, int rows, int cols, const double* s,

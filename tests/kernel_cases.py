@@ -72,6 +72,43 @@ def case_block_matvec(rt, case):
     return errs
 
 
+def case_block_matvec_big(rt, case=None, shape=None, ksplit=0):
+    """The large-rank path of K1 (three grouped contraction-GEMM launches, csrc/cgemm.cu) forced onto the fixture
+    cases, or onto a random local block of the given shape checked against einsum (reference src/tt_als.py:193)."""
+    old = rt.lib.ttipm_matvec_big_min_flops(0.0)
+    old_ks = rt.lib.ttipm_cgemm_force_ksplit(ksplit)
+    try:
+        if case is not None:
+            return case_block_matvec(rt, case)
+        r, R, nb, ranks = shape
+        rng = np.random.default_rng(5)
+        n = 4
+        A = {k: rng.standard_normal((s, n, n, S)) for k, (s, S) in ranks.items()}
+        P1 = {k: rng.standard_normal((r, s, r)) for k, (s, S) in ranks.items()}
+        P2 = {k: rng.standard_normal((R, S, R)) for k, (s, S) in ranks.items()}
+        x = rng.standard_normal((r, nb, n, R))
+        c = dict(A=A, transposes={(0, 1): (1, 0)}, aliases={(1, 2): (1, 3)} if nb == 4 else {})
+        bm = O.BlockMatrix({k: [v] for k, v in A.items()}, aliases=c["aliases"], transposes=c["transposes"])
+        want = O.block_local_product(bm, 0, P1, P2, x)
+        tl = full_terms(rt, c, P1, P2, False, False)
+        errs = {}
+        y, ss = K.block_matvec(tl, rt.to_device(x), nb, (r, R), want_norm=True, rt=rt)
+        errs["big_y"] = rel(rt.to_host(y), want)
+        errs["big_sumsq"] = rel(rt.to_host(ss).sum(), (want ** 2).sum())
+        # forward-unfolding layout (r, n, b, R) of the sweep, residual form
+        xf = np.ascontiguousarray(x.transpose(0, 2, 1, 3))
+        sub = rt.to_device(0.25 * want)
+        y2 = K.block_matvec(tl, rt.to_device(xf), nb, (r, R), x_layout="rnbR", sub=sub, rt=rt)
+        errs["big_rnbR_sub"] = rel(rt.to_host(y2), 0.75 * want)
+        rt.lib.ttipm_matvec_big_min_flops(1e30)
+        y3 = K.block_matvec(tl, rt.to_device(x), nb, (r, R), rt=rt)
+        errs["big_vs_fused"] = rel(rt.to_host(y), rt.to_host(y3))
+        return errs
+    finally:
+        rt.lib.ttipm_matvec_big_min_flops(old)
+        rt.lib.ttipm_cgemm_force_ksplit(old_ks)
+
+
 def case_phi(rt, case):
     c = load_blp_case(case)
     z, p = c["z"], c["p"]

@@ -19,6 +19,20 @@ def test_block_matvec(rt, case):
 
 
 @pytest.mark.parametrize("case", CASES)
+def test_block_matvec_grouped_gemm_path(rt, case):
+    """large-rank path of K1 (csrc/cgemm.cu) forced onto the fixture shapes: compressed variants, batch, sub, norms"""
+    KC.assert_small(KC.case_block_matvec_big(rt, case))
+
+
+@pytest.mark.parametrize("ksplit", [0, 3])
+def test_block_matvec_grouped_gemm_random(rt, ksplit):
+    ranks = {(0, 0): (2, 3), (0, 1): (1, 2), (1, 2): (1, 1), (2, 1): (3, 2), (2, 2): (2, 2)}
+    KC.assert_small(KC.case_block_matvec_big(rt, shape=(9, 7, 3, ranks), ksplit=ksplit))
+    if ksplit:
+        KC.assert_small(KC.case_block_matvec_big(rt, "eq_small", ksplit=ksplit))
+
+
+@pytest.mark.parametrize("case", CASES)
 def test_phi(rt, case):
     KC.assert_small(KC.case_phi(rt, case))
 

@@ -38,6 +38,23 @@ def test_gemm(rt):
     KC.assert_small(KC.case_gemm(rt))
 
 
+@pytest.mark.parametrize("case", CASES)
+def test_block_matvec_grouped_gemm_path(rt, case):
+    """large-rank path of K1 (csrc/cgemm.cu) forced onto the fixture shapes: compressed variants, batch, sub, norms"""
+    KC.assert_small(KC.case_block_matvec_big(rt, case))
+
+
+@pytest.mark.parametrize("ksplit", [0, 5])
+@pytest.mark.parametrize("r,R,nb,s", [(55, 55, 3, 5), (29, 44, 4, 10), (64, 64, 3, 8), (130, 97, 3, 17), (128, 128, 4, 16)])
+def test_block_matvec_grouped_gemm_vs_einsum(rt, r, R, nb, s, ksplit):
+    """128x128 / 64x64 DMMA tile kernels on ragged and on full shapes vs einsum of the reference equation; also
+    checks the fused small-block kernel against it where that one still fits shared memory"""
+    ranks = {(0, 0): (2, 3), (0, 1): (s, s - 1), (1, 2): (1, 1), (2, 1): (s, s), (2, 2): (s - 1, s)}
+    if nb == 4:
+        ranks.update({(3, 1): (1, 1), (3, 3): (2, 2)})
+    KC.assert_small(KC.case_block_matvec_big(rt, shape=(r, R, nb, ranks), ksplit=ksplit))
+
+
 @pytest.mark.parametrize("r,R,s", [(55, 55, 5), (29, 44, 10), (64, 64, 8)])
 def test_block_matvec_large_vs_oracle(rt, r, R, s):
     """Large-regime shapes (SURVEY 8a''): maxcut_13 r2 and graphm_3 r2 local blocks."""

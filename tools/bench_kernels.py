@@ -31,15 +31,22 @@ def time_cuda(fn, iters=50, warm=5):
 
 
 def main():
+    """K1 on traced shapes and on the scaled synthetic grid: fused one-CTA-per-slab kernel vs the grouped
+    contraction-GEMM path, CUDA events over back-to-back launches, against cuBLAS DGEMM measured here."""
     rt = get_runtime()
     rng = np.random.default_rng(0)
-    out = []
-    shapes = [("small", 4, 5, {(0, 0): 2, (0, 1): 1, (1, 2): 1, (2, 1): 4, (2, 2): 4}),
-              ("medium", 22, 22, {(0, 0): 3, (0, 1): 2, (1, 2): 1, (2, 1): 6, (2, 2): 6}),
-              ("maxcut13", 55, 55, {(0, 0): 2, (0, 1): 1, (1, 2): 1, (2, 1): 5, (2, 2): 5}),
-              ("graphm3", 29, 44, {(0, 0): 5, (0, 1): 10, (1, 2): 1, (2, 1): 1, (2, 2): 4}),
-              ("grid64", 64, 64, {(0, 0): 8, (0, 1): 8, (1, 2): 1, (2, 1): 8, (2, 2): 8}),
-              ("grid128", 128, 128, {(0, 0): 8, (0, 1): 8, (1, 2): 1, (2, 1): 8, (2, 2): 8})]
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    us = time_cuda(lambda: a @ a, iters=5, warm=2)
+    peak = 2.0 * n ** 3 / us * 1e-6          # TFLOP/s
+    print(json.dumps(dict(kernel="cublas_dgemm_4096", tflops=peak)), flush=True)
+    out = [dict(kernel="cublas_dgemm_4096", tflops=peak)]
+    eq = lambda s: {(0, 0): s, (0, 1): s, (1, 2): 1, (2, 1): s, (2, 2): s}
+    shapes = [("maxcut13", 55, 55, {(0, 0): 2, (0, 1): 1, (1, 2): 1, (2, 1): 5, (2, 2): 5}),
+              ("graphm3", 29, 44, {(0, 0): 5, (0, 1): 10, (1, 2): 1, (2, 1): 1, (2, 2): 4})]
+    for r in (64, 128, 256):
+        for s in (8, 16, 32):
+            shapes.append((f"grid_r{r}_s{s}", r, r, eq(s)))
     for name, r, R, ranks in shapes:
         dev = lambda a: rt.to_device(a)
         A = {k: dev(rng.standard_normal((s, 4, 4, s))) for k, s in ranks.items()}
@@ -54,22 +61,18 @@ def main():
             if (i, j) == (0, 1):
                 tl.add(P1[i, j].permute(2, 1, 0), A[i, j].permute(0, 2, 1, 3), P2[i, j].permute(2, 1, 0), 0, 1)
                 flops += term_flops(r, R, r, R, s, s)
-        try:
-            us = time_cuda(lambda: K.block_matvec(tl, x, 3, (r, R), rt=rt))
-            rec = dict(kernel="block_matvec", shape=name, r=r, R=R, us=us, gflops=flops / us * 1e-3, flops=flops)
-        except Exception as e:   # report, do not hide
-            rec = dict(kernel="block_matvec", shape=name, error=str(e))
-        print(json.dumps(rec), flush=True)
-        out.append(rec)
-        keys = list(ranks.keys())
-        core = dev(rng.standard_normal((r, 4, R)))
-        try:
-            us = time_cuda(lambda: K.phi_update([P1[k] for k in keys], [A[k] for k in keys], core, core, True, rt=rt))
-            rec = dict(kernel="phi_fwd", shape=name, us=us)
-        except Exception as e:
-            rec = dict(kernel="phi_fwd", shape=name, error=str(e))
-        print(json.dumps(rec), flush=True)
-        out.append(rec)
+        for path, thr in (("fused", 1e30), ("grouped_gemm", 0.0)):
+            old = rt.lib.ttipm_matvec_big_min_flops(thr)
+            try:
+                us = time_cuda(lambda: K.block_matvec(tl, x, 3, (r, R), rt=rt), iters=20, warm=3)
+                rec = dict(kernel="block_matvec", path=path, shape=name, r=r, R=R, us=us, tflops=flops / us * 1e-6,
+                           frac_of_dgemm=flops / us * 1e-6 / peak, flops=flops)
+            except Exception as e:   # report, do not hide
+                rec = dict(kernel="block_matvec", path=path, shape=name, error=str(e)[:200])
+            finally:
+                rt.lib.ttipm_matvec_big_min_flops(old)
+            print(json.dumps(rec), flush=True)
+            out.append(rec)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "bench_kernels.jsonl"), "w") as f:
         for rec in out:
