@@ -205,7 +205,7 @@ TT_DEV void tgemm(int M, int N, int K, const double* __restrict__ A, AxisMap aM,
     __syncthreads();
 }
 
-// One row of a memory-bound copy kernel: dst[j] = op(src[j]) for j = tx, tx + tw, ... < n, eight independent loads
+// One row of a memory-bound copy kernel: dst[j] = op(src[j]) for j = tx, tx + tw, ... < n, four independent loads
 // in flight per thread before the first store (dst and src never alias; src == nullptr writes zeros).
 // op: 0 copy, 1 multiply by s, 2 divide by s.
 TT_DEV void row_stream(double* __restrict__ dst, const double* __restrict__ src, int n, int tx, int tw, int op, double s) {
@@ -213,17 +213,13 @@ TT_DEV void row_stream(double* __restrict__ dst, const double* __restrict__ src,
         for (int j = tx; j < n; j += tw) dst[j] = 0.0;
         return;
     }
-    int j = tx;
-    for (; j + 7 * tw < n; j += 8 * tw) {
-        double v[8];
+    for (int j = tx; j < n; j += 4 * tw) {
+        double v[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = src[j + u * tw];
+        for (int u = 0; u < 4; ++u) v[u] = j + u * tw < n ? src[j + u * tw] : 0.0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) dst[j + u * tw] = op == 0 ? v[u] : (op == 1 ? v[u] * s : v[u] / s);
-    }
-    for (; j < n; j += tw) {
-        const double v = src[j];
-        dst[j] = op == 0 ? v : (op == 1 ? v * s : v / s);
+        for (int u = 0; u < 4; ++u)
+            if (j + u * tw < n) dst[j + u * tw] = op == 0 ? v[u] : (op == 1 ? v[u] * s : v[u] / s);
     }
 }
 

@@ -104,17 +104,28 @@ TT_GLOBAL void k_ewise(const EwParams p) {
     double* scr = (double*)smem_raw;
     double ss = 0.0;
     if (p.rows == 1) {
-        // contiguous operands: flat grid-stride loop, eight independent elements per thread and trip
+        // contiguous operands: flat grid-stride loop, W independent elements per thread and trip (W = 8 for the
+        // reduction-only form, whose grid is capped by the 256 partial-sum slots; 4 otherwise)
         const long tot = p.inner, stride = (long)gridDim.x * blockDim.x;
         long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-        for (; i + 7 * stride < tot; i += 8 * stride) {
-            double v[8];
+        if (p.sumsq) {
+            for (; i + 7 * stride < tot; i += 8 * stride) {
+                double v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = ew_value(p, i + u * stride, i + u * stride, i + u * stride, i + u * stride);
+                for (int u = 0; u < 8; ++u) v[u] = ew_value(p, i + u * stride, i + u * stride, i + u * stride, i + u * stride);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (p.out) p.out[i + u * stride] = v[u];
-                ss += v[u] * v[u];
+                for (int u = 0; u < 8; ++u) {
+                    if (p.out) p.out[i + u * stride] = v[u];
+                    ss += v[u] * v[u];
+                }
+            }
+        } else {
+            for (; i + 3 * stride < tot; i += 4 * stride) {
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = ew_value(p, i + u * stride, i + u * stride, i + u * stride, i + u * stride);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) p.out[i + u * stride] = v[u];
             }
         }
         for (; i < tot; i += stride) {
@@ -239,7 +250,7 @@ extern "C" int ttipm_ewise(int rows, int inner, double alpha, const double* a, i
         const long rows_per = bt >> p.tw_shift;
         blocks = (rows + rows_per - 1) / rows_per;
     } else {
-        blocks = (blocks + 7) / 8;                   // eight elements per thread and trip
+        blocks = sumsq ? (blocks + 7) / 8 : (blocks + 3) / 4;       // elements per thread and trip
     }
     // the sum-of-squares partials have EW_MAX_PARTS slots; without them fill the machine
     const long cap = sumsq ? EW_MAX_PARTS : (long)dev_info().sms * 8;
