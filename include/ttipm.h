@@ -68,6 +68,10 @@ int ttipm_cgemm_force_ksplit(int ksplit);
 /* Tuning hook: force the tile shape of the grouped-GEMM launches (0 = 128x128, 1 = 128x64, 2 = 64x64, -1 = automatic).
  * Returns the previous value; an argument below -1 only queries. */
 int ttipm_cgemm_force_cfg(int cfg);
+/* Tuning / test hook: allow (1, default) or forbid (0) the two-doubles-per-cp.async operand loads of the grouped-GEMM
+ * path (used where the contiguous axis has unit stride and 16-byte aligned rows).  Returns the previous value; a
+ * negative argument only queries. */
+int ttipm_cgemm_vector_loads(int on);
 
 /* K4 -- diag[l,m,L] = sum_s,S P1[l,s,l] A[s,m,m,S] P2[L,S,L]   (reference src/tt_ipm.py:191, :292);
  * if invert != 0 stores 1/diag (the inv_I of the Schur reduction). */

@@ -33,7 +33,15 @@ static long cg_tiles(const CgParams& p, int cfg) {
     return t * p.nbatch;
 }
 
+static int g_vec_enabled = 1;
+
 long cg_plan(CgParams& p, int sms) {
+    int nseg_total = 0;
+    for (int q = 0; q < p.nprob; ++q) nseg_total = imax(nseg_total, p.prob[q].seg0 + p.prob[q].nseg);
+    for (int e = 0; e < nseg_total; ++e) {
+        if (g_vec_enabled) cg_mark_vec(p.seg[e]);
+        else p.seg[e].a_vec = p.seg[e].b_vec = 0;
+    }
     // largest tile shape that still gives every SM two tiles and does not waste most of a tile on a thin problem
     int min_m = 1 << 30, min_n = 1 << 30;
     for (int q = 0; q < p.nprob; ++q) {
@@ -245,6 +253,12 @@ int mv_big(const MvTerm* t, int nterms, int l, int L, int r, int R, int nm, int 
 }  // namespace ttipm
 
 using namespace ttipm;
+
+extern "C" int ttipm_cgemm_vector_loads(int on) {
+    const int old = g_vec_enabled;
+    if (on >= 0) g_vec_enabled = on ? 1 : 0;
+    return old;
+}
 
 extern "C" int ttipm_cgemm_force_cfg(int cfg) {
     const int old = g_force_cfg;

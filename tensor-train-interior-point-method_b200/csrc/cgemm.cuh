@@ -32,6 +32,8 @@ struct CgSeg {
     long a_batch, b_batch;
     int K;
     int a_kfast, b_kfast;   // 1: the K axis is the contiguous one in memory (tile stored [m][k]); 0: tile stored [k][m]
+    int a_vec, b_vec;       // 1: the contiguous axis has unit stride and every row / column start is 16-byte aligned:
+                            //    the loader moves two doubles per cp.async (set by cg_mark_vec on the host)
 };
 
 struct CgProb {
@@ -80,11 +82,20 @@ TT_DEV void cg_cp8(double* dst_smem, const double* src, bool valid) {
     const int bytes = valid ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
+TT_DEV void cg_cp16(double* dst_smem, const double* src, int nvalid) {       // nvalid in {0, 1, 2} doubles, rest zero-filled
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int bytes = 8 * nvalid;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
 TT_DEV void cg_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 TT_DEV void cg_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #else
 TT_DEV void cg_cp8(double* dst_smem, const double* src, bool valid) { *dst_smem = valid ? *src : 0.0; }
+TT_DEV void cg_cp16(double* dst_smem, const double* src, int nvalid) {
+    dst_smem[0] = nvalid > 0 ? src[0] : 0.0;
+    dst_smem[1] = nvalid > 1 ? src[1] : 0.0;
+}
 TT_DEV void cg_commit() {}
 template <int N>
 TT_DEV void cg_wait() {}
@@ -151,33 +162,37 @@ TT_DEV void cg_tile(const CgParams& p, const CgProb& pr, int batch, int m0, int 
             abase = (long)batch * s.a_batch;
             bbase = (long)batch * s.b_batch;
             avalid = bvalid = 0;
+            // row (column) offsets of this thread's copies; the thread <-> element mapping depends on the layout
+            // (K-fast / M-fast) and on the copy width (one or two doubles)
             if (s.a_kfast) {
+                const int rpp = s.a_vec ? NT / 8 : NT / 16, r0 = s.a_vec ? tid >> 3 : tid >> 4;
 #pragma unroll
                 for (int q = 0; q < A_PASS; ++q) {
-                    const int m = m0 + (tid >> 4) + q * (NT / 16);
-                    const bool ok = m < pr.M;
+                    const int m = m0 + r0 + q * rpp;
+                    const bool ok = m < pr.M && r0 + q * rpp < BM;
                     aoff[q] = ok ? axoff(s.aM, m) : 0;
                     avalid |= ok ? (1u << q) : 0u;
                 }
             } else {
-                const int m = m0 + tid % BM;
-                const bool ok = m < pr.M;
-                aoff[0] = ok ? axoff(s.aM, m) : 0;
-                avalid = ok ? 1u : 0u;
+                const int i = s.a_vec ? (tid % (BM / 2)) * 2 : tid % BM;
+                const int left = pr.M - (m0 + i);
+                aoff[0] = left > 0 ? axoff(s.aM, m0 + i) : 0;
+                avalid = left > 1 ? 2u : (left > 0 ? 1u : 0u);          // valid elements of a 2-wide copy
             }
             if (s.b_kfast) {
+                const int rpp = s.b_vec ? NT / 8 : NT / 16, r0 = s.b_vec ? tid >> 3 : tid >> 4;
 #pragma unroll
                 for (int q = 0; q < B_PASS; ++q) {
-                    const int n = n0 + (tid >> 4) + q * (NT / 16);
-                    const bool ok = n < pr.N;
+                    const int n = n0 + r0 + q * rpp;
+                    const bool ok = n < pr.N && r0 + q * rpp < BN;
                     boff[q] = ok ? axoff(s.bN, n) : 0;
                     bvalid |= ok ? (1u << q) : 0u;
                 }
             } else {
-                const int n = n0 + tid % BN;
-                const bool ok = n < pr.N;
-                boff[0] = ok ? axoff(s.bN, n) : 0;
-                bvalid = ok ? 1u : 0u;
+                const int i = s.b_vec ? (tid % (BN / 2)) * 2 : tid % BN;
+                const int left = pr.N - (n0 + i);
+                boff[0] = left > 0 ? axoff(s.bN, n0 + i) : 0;
+                bvalid = left > 1 ? 2u : (left > 0 ? 1u : 0u);
             }
         }
         const int slot = step % CG_STAGES;
@@ -188,7 +203,16 @@ TT_DEV void cg_tile(const CgParams& p, const CgProb& pr, int batch, int m0, int 
         const int krem = s.K - kt * CG_BK;          // valid k's in this tile
         const double* Ab = s.A + abase;
         const double* Bb = s.B + bbase;
-        if (s.a_kfast) {
+        if (s.a_kfast && s.a_vec) {
+            const int kk = (tid & 7) * 2, i0 = tid >> 3;
+            const int nv = imin(2, krem - kk);
+            const int ko = ka[kk];
+#pragma unroll
+            for (int q = 0; q < A_PASS / 2; ++q) {
+                const bool ok = nv > 0 && ((avalid >> q) & 1u);
+                cg_cp16(As + (i0 + q * (NT / 8)) * LDK + kk, Ab + (ok ? aoff[q] + ko : 0), ok ? nv : 0);
+            }
+        } else if (s.a_kfast) {
             const int kk = tid & 15, i0 = tid >> 4;
             const bool kok = kk < krem;
             const int ko = ka[kk];
@@ -197,16 +221,33 @@ TT_DEV void cg_tile(const CgParams& p, const CgProb& pr, int batch, int m0, int 
                 const bool ok = kok && ((avalid >> q) & 1u);
                 cg_cp8(As + (i0 + q * (NT / 16)) * LDK + kk, Ab + (ok ? aoff[q] + ko : 0), ok);
             }
+        } else if (s.a_vec) {
+            const int i = (tid % (BM / 2)) * 2, kq = tid / (BM / 2);
+#pragma unroll
+            for (int q = 0; q < A_PASS / 2; ++q) {
+                const int kk = kq + q * (NT / (BM / 2));
+                const int nv = kk < krem ? (int)avalid : 0;
+                cg_cp16(As + kk * (BM + 4) + i, Ab + (nv ? aoff[0] + ka[kk] : 0), nv);
+            }
         } else {
             const int i = tid % BM, kq = tid / BM;
 #pragma unroll
             for (int q = 0; q < A_PASS; ++q) {
                 const int kk = kq + q * (NT / BM);
-                const bool ok = (avalid & 1u) && kk < krem;
+                const bool ok = avalid && kk < krem;
                 cg_cp8(As + kk * (BM + 4) + i, Ab + (ok ? aoff[0] + ka[kk] : 0), ok);
             }
         }
-        if (s.b_kfast) {
+        if (s.b_kfast && s.b_vec) {
+            const int kk = (tid & 7) * 2, i0 = tid >> 3;
+            const int nv = imin(2, krem - kk);
+            const int ko = kb[kk];
+#pragma unroll
+            for (int q = 0; q < (B_PASS + 1) / 2; ++q) {
+                const bool ok = nv > 0 && ((bvalid >> q) & 1u);
+                if (i0 + q * (NT / 8) < BN) cg_cp16(Bs + (i0 + q * (NT / 8)) * LDK + kk, Bb + (ok ? boff[q] + ko : 0), ok ? nv : 0);
+            }
+        } else if (s.b_kfast) {
             const int kk = tid & 15, i0 = tid >> 4;
             const bool kok = kk < krem;
             const int ko = kb[kk];
@@ -215,12 +256,20 @@ TT_DEV void cg_tile(const CgParams& p, const CgProb& pr, int batch, int m0, int 
                 const bool ok = kok && ((bvalid >> q) & 1u);
                 cg_cp8(Bs + (i0 + q * (NT / 16)) * LDK + kk, Bb + (ok ? boff[q] + ko : 0), ok);
             }
+        } else if (s.b_vec) {
+            const int i = (tid % (BN / 2)) * 2, kq = tid / (BN / 2);
+#pragma unroll
+            for (int q = 0; q < (B_PASS + 1) / 2; ++q) {
+                const int kk = kq + q * (NT / (BN / 2));
+                const int nv = kk < krem ? (int)bvalid : 0;
+                if (kk < CG_BK) cg_cp16(Bs + kk * (BN + 4) + i, Bb + (nv ? boff[0] + kb[kk] : 0), nv);
+            }
         } else {
             const int i = tid % BN, kq = tid / BN;
 #pragma unroll
             for (int q = 0; q < B_PASS; ++q) {
                 const int kk = kq + q * (NT / BN);
-                const bool ok = (bvalid & 1u) && kk < krem;
+                const bool ok = bvalid && kk < krem;
                 cg_cp8(Bs + kk * (BN + 4) + i, Bb + (ok ? boff[0] + kb[kk] : 0), ok);
             }
         }
@@ -365,6 +414,16 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_cg_reduce(const CgReduceParam
     }
 }
 #endif
+
+// host: mark the operands a loader may move two doubles at a time (unit stride along the contiguous axis, every other
+// stride, the batch stride and the base address multiples of 16 bytes)
+static inline bool cg_even(const AxisMap& a) { return (a.n1 == TT_AX_BIG || a.s0 % 2 == 0) && a.s1 % 2 == 0; }
+static inline bool cg_unit(const AxisMap& a) { return a.n1 == TT_AX_BIG && a.s1 == 1; }
+static inline void cg_mark_vec(CgSeg& s) {
+    const bool a_al = ((uintptr_t)s.A % 16 == 0) && s.a_batch % 2 == 0, b_al = ((uintptr_t)s.B % 16 == 0) && s.b_batch % 2 == 0;
+    s.a_vec = a_al && (s.a_kfast ? (cg_unit(s.aK) && cg_even(s.aM)) : (cg_unit(s.aM) && cg_even(s.aK)));
+    s.b_vec = b_al && (s.b_kfast ? (cg_unit(s.bK) && cg_even(s.bN)) : (cg_unit(s.bN) && cg_even(s.bK)));
+}
 
 // host: tile counts / job ranges for a tile shape; returns the number of jobs per batch entry
 static inline int cg_plan_tiles(CgParams& p, int BM, int BN) {

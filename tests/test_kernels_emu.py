@@ -32,6 +32,18 @@ def test_block_matvec_grouped_gemm_random(rt, ksplit):
         KC.assert_small(KC.case_block_matvec_big(rt, "eq_small", ksplit=ksplit))
 
 
+@pytest.mark.parametrize("vec", [1, 0])
+def test_block_matvec_grouped_gemm_vector_loads(rt, vec):
+    """even ranks / aligned operands take the two-doubles-per-cp.async loaders; same numbers with them forbidden"""
+    ranks = {(0, 0): (2, 2), (0, 1): (2, 4), (1, 2): (2, 2), (2, 1): (4, 2), (2, 2): (2, 2)}
+    old = rt.lib.ttipm_cgemm_vector_loads(vec)
+    try:
+        KC.assert_small(KC.case_block_matvec_big(rt, shape=(8, 6, 3, ranks)))
+        KC.assert_small(KC.case_block_matvec_big(rt, shape=(6, 10, 3, ranks), ksplit=2))
+    finally:
+        rt.lib.ttipm_cgemm_vector_loads(old)
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_phi(rt, case):
     KC.assert_small(KC.case_phi(rt, case))

@@ -45,7 +45,8 @@ def test_block_matvec_grouped_gemm_path(rt, case):
 
 
 @pytest.mark.parametrize("ksplit", [0, 5])
-@pytest.mark.parametrize("r,R,nb,s", [(55, 55, 3, 5), (29, 44, 4, 10), (64, 64, 3, 8), (130, 97, 3, 17), (128, 128, 4, 16)])
+@pytest.mark.parametrize("r,R,nb,s", [(55, 55, 3, 5), (29, 44, 4, 10), (64, 64, 3, 8), (130, 97, 3, 17), (128, 128, 4, 16),
+                                      (96, 130, 3, 9), (66, 34, 4, 6)])
 def test_block_matvec_grouped_gemm_vs_einsum(rt, r, R, nb, s, ksplit):
     """128x128 / 64x64 DMMA tile kernels on ragged and on full shapes vs einsum of the reference equation; also
     checks the fused small-block kernel against it where that one still fits shared memory"""

@@ -40,6 +40,15 @@ def main():
                 flops += f
         x = up(rng.standard_normal((r, 3, 4, r)))
         op = sharded.ShardedBlockMatvec(terms, 3, (r, r), rt=rt)
+        if "SHARD_FAKE_WORLD" in os.environ:                 # single-GPU debugging of one rank's slab of a larger job
+            fw = int(os.environ["SHARD_FAKE_WORLD"])
+            op.world, op.rank = fw, fw - 1
+            op.lo, op.hi, op.per = sharded.slab(r, fw - 1, fw)
+            op.terms = sharded.K.TermList()
+            for t in terms:
+                op.terms.add(t[0], t[1], t[2][op.lo:op.hi], t[3], t[4])
+            op.world = 1
+            op.L = op.per
         for _ in range(3):
             y = op(x)
         torch.cuda.synchronize(dev)
