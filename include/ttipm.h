@@ -142,6 +142,17 @@ int ttipm_local_lgmres(int ineq, const ttipm_term* K00, const ttipm_term* K01, c
  * matrices use one CTA per matrix.  The setter returns the previous threshold (default 17); min_dim <= 0 only queries. */
 int ttipm_linalg_coop_min_dim(int min_dim);
 
+/* Tall SVDs (M >= N) are preconditioned by three QR factorisations (A = Q1 R1, R1^T = Q2 R2, R2^T = Q3 R3; Jacobi on the
+ * rows of R3 with a K x K accumulator): 1 (default) / 0 = single QR with the K x M accumulator.  Returns the previous
+ * setting; a negative argument only queries. */
+int ttipm_linalg_tall_triple_qr(int on);
+/* Rows of the Jacobi iteration whose norm is below factor * eps * ||R||_F are treated as numerically zero and left
+ * alone (fewer sweeps on strongly graded unfoldings; singular values below that level then carry an absolute error of
+ * that size, U stays orthonormal and U W = A).  Default 0 = off: every row pair is orthogonalised to relative accuracy,
+ * which is what the rank decisions of the AMEn sweep were validated with.  Returns the previous factor; a negative
+ * argument only queries. */
+double ttipm_linalg_noise_floor(double factor);
+
 /* Householder QR, A (M x N, strided) = Q (M x K) R (K x N), K = min(M, N); Q, R contiguous row-major.
  * Replaces scipy.linalg.qr(mode="economic") at reference cy_src/tt_ops_cy.pyx:147, src/tt_als.py:358, :482.
  * workspace: ttipm_qr_workspace() doubles (required). */

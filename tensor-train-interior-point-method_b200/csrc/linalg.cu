@@ -16,7 +16,12 @@
 //   Q       reflectors are staged panel by panel in shared memory and applied to register-resident vectors
 //           (unit vectors -> rows of Q^T, or [g; 0] -> rows of G Q^T), one vector per warp, no grid barrier.
 //   Jacobi  QR-preconditioned BLOCK one-sided Jacobi on the rows of the triangular factor R (K x K):
-//           tall A = Q R        -> rotate rows of R, accumulator starts from Q^T   (rows end as U^T)
+//           tall A = Q1 R1, R1^T = Q2 R2, R2^T = Q3 R3 -> rotate rows of R3, accumulator starts from Q3^T (K x K),
+//                                  U = Q1 (accumulator)^T, W = (rotated rows) Q2^T at the end
+//                                  (each QR of the transpose grades the factor further: on the sweep's real
+//                                  unfoldings rows of R1 need 27-31 sweeps, rows of R3 ~10; rows are 2K long
+//                                  instead of K + M).  ttipm_linalg_tall_triple_qr(0) selects the single-QR form
+//                                  A = Q R -> rotate rows of R, accumulator starts from Q^T.
 //           wide A^T = Q1 R1, R1^T = Q2 R2 -> rotate rows of R2, accumulator starts from Q2^T,
 //                                  W = (rotated rows) Q1^T at the end
 //           (rows of an unpreconditioned wide matrix need 40-50 sweeps, rows of R need ~10).
@@ -42,11 +47,14 @@ struct LinParams {
     double* ws;          // [nbatch x 40 doubles: sweep flags + barrier][nbatch x ws_per]
     long ws_per;
     long oW1, oTau1, oW2, oTau2, oG, oJt, oSv;      // offsets inside one batch workspace
+    long oW3, oTau3;     // third factor of the tall SVD
+    int triple;          // tall SVD preconditioned by three QR factorisations (accumulator K x K)
     long oPg;            // >= 0: the reflector panel lives in the batch workspace (columns too long for shared memory)
     int M1, N1;          // first QR: M x N (tall, square, QR mode) or N x M (wide SVD, factors A^T)
     int Mj;              // accumulator row length
     int nb;              // Jacobi block rows
     int resident;        // single CTA with every row [R | accumulator] in shared memory
+    double floor_factor; // rows below floor_factor * eps * ||R||_F are left alone by the Jacobi iteration (0 = off)
     int ldp;             // panel leading dimension in shared memory
     int oOrd, oSvS, oTaus, oP;   // shared-memory offsets (doubles)
     int nbatch;
@@ -265,7 +273,14 @@ TT_DEV void lin_apply_q(LinCtx& c, const double* W, const double* tau, int Mq, i
 }
 
 // orthogonalise two rows held in shared memory: [row of R (K) | accumulator row (Mj)], total length Ls
-TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, int lane) {
+//
+// `floor2` = (eps * ||R||_F)^2: a row whose norm has dropped below the rounding level of the largest singular value is
+// numerically zero -- it is left alone (the unfoldings of the AMEn sweep are strongly graded: at maxcut_13 half of
+// the singular values sit 1e-14 below the largest, and orthogonalising those noise rows against each other to full
+// RELATIVE accuracy cost 27-31 sweeps instead of the ~10 the significant part needs).  U stays orthonormal and
+// U * W = A holds regardless (only rotations are applied); singular values above the floor are unaffected, the ones
+// below it carry an absolute error of eps * sigma_max like LAPACK's.
+TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, double floor2, int lane) {
     double saa = 0.0, sbb = 0.0, sab = 0.0;
 #pragma unroll 4
     for (int i = lane; i < K; i += 32) {
@@ -286,7 +301,7 @@ TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, 
     sbb = warp_sum(sbb);
     sab = warp_sum(sab);
 #endif
-    if (!(sab * sab > tol2 * saa * sbb)) return false;
+    if (!(sab * sab > tol2 * saa * sbb) || fmin(saa, sbb) <= floor2) return false;
     // tan of the rotation angle: zeta = (sbb - saa) / (2 sab), tg = sign(zeta) / (|zeta| + sqrt(1 + zeta^2))
     const double d = sbb - saa;
     const double tg = 2.0 * sab / (d + copysign(sqrt(d * d + 4.0 * sab * sab), d));
@@ -301,6 +316,19 @@ TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, 
     return true;
 }
 
+// (eps * ||G||_F)^2 of the K x K matrix G in global memory, computed redundantly by every CTA
+TT_DEV double lin_noise_floor2(LinCtx& c, const double* G, int K) {
+    double s = 0.0;
+    for (long i = threadIdx.x; i < (long)K * K; i += blockDim.x) {
+        const double v = ld_cg(G + i);
+        s += v * v;
+    }
+    __syncthreads();
+    s = block_sum(s, c.smem);
+    const double e = 2.220446049250313e-16 * c.p.floor_factor;
+    return e * e * s;
+}
+
 // block one-sided Jacobi on the rows of G (K x K) with accumulator Jt (K x Mj), both row-major in global memory.
 // Ends with a grid barrier (all rows globally visible).  Returns the number of sweeps.
 TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flags, long long* tm) {
@@ -311,6 +339,7 @@ TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flag
     double* rowsS = c.smem + c.p.oTaus;
     int sweeps = 0;
     if (K < 2) return 0;
+    const double floor2 = lin_noise_floor2(c, G, K);
     for (; sweeps < 60; ++sweeps) {
         for (int t = 0; t < rounds; ++t) {
             for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
@@ -360,7 +389,7 @@ TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flag
                             if (x >= cnt || y >= cnt) continue;
                             if (x > y) { const int z = x; x = y; y = z; }
                             rot |= lin_jacobi_pair(rowsS + (long)(sel * nb + x) * Ls, rowsS + (long)(sel * nb + y) * Ls, K, Ls,
-                                                   tol2, lane);
+                                                   tol2, floor2, lane);
                         }
                         __syncthreads();
                     }
@@ -370,7 +399,7 @@ TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flag
                         for (int i = wid; i < nb; i += nw) {
                             const int jb = (i + u) % nb;
                             if (i >= na || jb >= nbb) continue;
-                            rot |= lin_jacobi_pair(rowsS + (long)i * Ls, rowsS + (long)(nb + jb) * Ls, K, Ls, tol2, lane);
+                            rot |= lin_jacobi_pair(rowsS + (long)i * Ls, rowsS + (long)(nb + jb) * Ls, K, Ls, tol2, floor2, lane);
                         }
                         __syncthreads();
                     }
@@ -415,6 +444,7 @@ TT_DEV int lin_jacobi_resident(LinCtx& c, double* G, double* Jt, int K, int Mj) 
     int* rotated = (int*)(c.smem + 36);
     double* rowsS = c.smem + c.p.oTaus;
     if (K < 2) return 0;
+    const double floor2 = lin_noise_floor2(c, G, K);
     __syncthreads();
     for (int row = wid; row < K; row += nw) {
         double* dstr = rowsS + (long)row * Ls;
@@ -439,7 +469,7 @@ TT_DEV int lin_jacobi_resident(LinCtx& c, double* G, double* Jt, int K, int Mj) 
                 }
                 if (x >= K || y >= K) continue;
                 if (x > y) { const int z = x; x = y; y = z; }
-                rot |= lin_jacobi_pair(rowsS + (long)x * Ls, rowsS + (long)y * Ls, K, Ls, tol2, lane);
+                rot |= lin_jacobi_pair(rowsS + (long)x * Ls, rowsS + (long)y * Ls, K, Ls, tol2, floor2, lane);
             }
             __syncthreads();
         }
@@ -503,7 +533,7 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
     const double* Wq = W1;      // factor whose R is rotated and whose Q^T seeds the accumulator
     const double* tq = tau1;
     int Mq = M1;
-    if (wide) {
+    if (wide || p.triple) {
         // L = R1^T (K x K lower triangular), column-major working copy, second QR
         for (long i = gtid; i < (long)K * K; i += gth) {
             const long row = i % K, col = i / K;
@@ -513,6 +543,21 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
         lin_qr_factor(c, W2, tau2, K, K);
         Wq = W2;
         tq = tau2;
+        Mq = K;
+    }
+    if (p.triple) {
+        // tall: a third factorisation R2^T = Q3 R3 puts the accumulator back on the U side:
+        //   A = Q1 R1 = Q1 R2^T Q2^T = (Q1 Q3) R3 Q2^T,  rows of R3 rotated, accumulator starts from Q3^T (K x K)
+        double* W3 = ws + p.oW3;
+        double* tau3 = ws + p.oTau3;
+        for (long i = gtid; i < (long)K * K; i += gth) {
+            const long row = i % K, col = i / K;
+            W3[i] = col <= row ? ld_cg(W2 + col + row * K) : 0.0;
+        }
+        c.sync();
+        lin_qr_factor(c, W3, tau3, K, K);
+        Wq = W3;
+        tq = tau3;
         Mq = K;
     }
     const long long t_qr = lin_now();
@@ -550,8 +595,14 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
     __syncthreads();
     double* S = p.S + (long)batch * K;
     for (long i = gtid; i < K; i += gth) S[i] = svS[ord[i]];
-    for (long i = gtid; i < (long)M * K; i += gth) U[i] = ld_cg(Jt + (long)ord[i % K] * Mj + i / K);
-    if (!wide) {
+    if (p.triple) {
+        lin_apply_q(c, W1, tau1, M1, K, K, 1, Jt, ord, U, 1, K);               // U columns = Q1 [(Q3 J) column; 0]
+        lin_apply_q(c, W2, tau2, K, K, K, 1, G, ord, Wt, N, 1);                // W rows = Q2 g  (N == K)
+    } else {
+        for (long i = gtid; i < (long)M * K; i += gth) U[i] = ld_cg(Jt + (long)ord[i % K] * Mj + i / K);
+    }
+    if (p.triple) {
+    } else if (!wide) {
         for (long i = gtid; i < (long)K * N; i += gth) Wt[i] = ld_cg(G + (long)ord[i / N] * K + i % N);
     } else {
         lin_apply_q(c, W1, tau1, M1, K, K, 1, G, ord, Wt, N, 1);               // W rows = Q1 [g; 0]
@@ -576,6 +627,8 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
 
 static int g_coop_min_dim = 17;
 static int g_resident_max_dim = 32;
+static double g_floor_factor = 0.0;
+static int g_tall_triple_qr = 1;
 
 struct LinPlan {
     LinParams p;
@@ -591,14 +644,18 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
     const long K = imin(M, N);
     const bool wide = mode == 0 && M < N;
     p.M = M; p.N = N; p.mode = mode; p.nbatch = nbatch;
+    p.floor_factor = g_floor_factor;
     p.M1 = wide ? N : M;
     p.N1 = wide ? M : N;
-    p.Mj = wide ? (int)K : M;
+    p.triple = (mode == 0 && !wide && g_tall_triple_qr) ? 1 : 0;
+    p.Mj = (wide || p.triple) ? (int)K : M;
     long o = 0;
     p.oW1 = o; o += (long)M * N;
     p.oTau1 = o; o += K;
-    p.oW2 = o; o += wide ? K * K : 0;
-    p.oTau2 = o; o += wide ? K : 0;
+    p.oW2 = o; o += (wide || p.triple) ? K * K : 0;
+    p.oTau2 = o; o += (wide || p.triple) ? K : 0;
+    p.oW3 = o; o += p.triple ? K * K : 0;
+    p.oTau3 = o; o += p.triple ? K : 0;
     p.oG = o; o += mode == 0 ? K * K : 0;
     p.oJt = o; o += mode == 0 ? K * p.Mj : 0;
     p.oSv = o; o += K;
@@ -691,6 +748,18 @@ using namespace ttipm;
 extern "C" int ttipm_linalg_coop_min_dim(int min_dim) {
     const int old = g_coop_min_dim;
     if (min_dim > 0) g_coop_min_dim = min_dim;
+    return old;
+}
+
+extern "C" int ttipm_linalg_tall_triple_qr(int on) {
+    const int old = g_tall_triple_qr;
+    if (on >= 0) g_tall_triple_qr = on ? 1 : 0;
+    return old;
+}
+
+extern "C" double ttipm_linalg_noise_floor(double factor) {
+    const double old = g_floor_factor;
+    if (factor >= 0.0) g_floor_factor = factor;
     return old;
 }
 

@@ -226,9 +226,15 @@ def case_lgmres(rt, case, grid_hint=0, restart=None, shift=8.0, rtol=1e-5, max_i
 
 
 def case_qr_svd(rt, shapes=((7, 5), (5, 7), (6, 6), (12, 3), (3, 12), (1, 4), (4, 1), (20, 12)), coop_min_dim=None,
-                graded=False):
+                graded=False, noise_floor=None):
     """QR / left-SVD parity (gauge-aware): reconstruction, orthogonality, singular values.
     coop_min_dim forces the cooperative multi-CTA kernel for matrices with min(M, N) >= that value."""
+    if noise_floor is not None:
+        oldf = rt.lib.ttipm_linalg_noise_floor(float(noise_floor))
+        try:
+            return case_qr_svd(rt, shapes, coop_min_dim, graded)
+        finally:
+            rt.lib.ttipm_linalg_noise_floor(oldf)
     if coop_min_dim is not None:
         old = rt.lib.ttipm_linalg_coop_min_dim(int(coop_min_dim))
         try:
@@ -240,9 +246,17 @@ def case_qr_svd(rt, shapes=((7, 5), (5, 7), (6, 6), (12, 3), (3, 12), (1, 4), (4
     errs = {}
     for (M, N) in shapes:
         a = rng.standard_normal((M, N))
-        if graded:                              # singular values spanning 16 decades, like a TT unfolding before truncation
+        if graded == "plateau":
+            # the spectrum of the sweep's real unfoldings (traced at maxcut_13): a third of the singular values decays
+            # over 9 decades, the rest is a rounding-noise plateau 1e-14 below the largest
+            Kp = min(M, N)
+            u_, _ = np.linalg.qr(rng.standard_normal((M, Kp)))
+            v_, _ = np.linalg.qr(rng.standard_normal((N, Kp)))
+            sv = np.concatenate([np.logspace(0, -9, (Kp + 2) // 3), 1e-14 * rng.uniform(0.1, 1.0, Kp - (Kp + 2) // 3)])
+            a = 12000.0 * (u_ * sv) @ v_.T
+        elif graded:                            # singular values spanning 16 decades, like a TT unfolding before truncation
             a = a * np.logspace(0, -16, N)[None, :]
-        if M >= 6 and N >= 5:
+        if M >= 6 and N >= 5 and graded != "plateau":
             a[:, -1] = a[:, 0] * 2.0            # exactly rank deficient: zero singular value
         Kk = min(M, N)
         at = rt.to_device(a.T.copy()).t()       # strided input view
@@ -253,6 +267,8 @@ def case_qr_svd(rt, shapes=((7, 5), (5, 7), (6, 6), (12, 3), (3, 12), (1, 4), (4
         U, S, W = (rt.to_host(t) for t in K.svd_left(at, rt=rt))
         sref = sla.svd(a, compute_uv=False)
         errs[f"svd_s{M}x{N}"] = float(np.max(np.abs(S - sref)) / sref[0])
+        sig = sref > 1e-10 * sref[0]            # significant part: relative agreement (LAPACK's own accuracy there is ~1e-6)
+        errs[f"svd_srel{M}x{N}"] = max(0.0, float(np.max(np.abs(S[sig] / sref[sig] - 1.0))) - 1e-5)
         errs[f"svd_rec{M}x{N}"] = rel(U @ W, a)
         errs[f"svd_orth{M}x{N}"] = float(np.linalg.norm(U.T @ U - np.eye(Kk)))
         errs[f"svd_w{M}x{N}"] = float(np.max(np.abs(np.linalg.norm(W, axis=1) - S)) / sref[0])

@@ -94,6 +94,23 @@ def test_qr_svd(rt):
                                                (88, 66), (220, 165), (165, 220), (40, 300))), tol=1e-11)
 
 
+def test_svd_tall_single_qr_form(rt):
+    """ttipm_linalg_tall_triple_qr(0): the single-QR form of the tall SVD (K x M accumulator) stays available"""
+    old = rt.lib.ttipm_linalg_tall_triple_qr(0)
+    try:
+        KC.assert_small(KC.case_qr_svd(rt, shapes=((20, 12), (88, 66), (220, 165), (440, 330))), tol=1e-11)
+        KC.assert_small(KC.case_qr_svd(rt, shapes=((20, 12), (88, 66)), coop_min_dim=1, graded=True), tol=1e-11)
+    finally:
+        rt.lib.ttipm_linalg_tall_triple_qr(old)
+
+
+def test_svd_noise_plateau(rt):
+    """strongly graded unfoldings with a rounding-noise plateau (the sweep's real spectrum): rows below eps * ||R||_F are
+    left alone by the Jacobi iteration; U stays orthonormal, U W = A, significant singular values agree with LAPACK"""
+    KC.assert_small(KC.case_qr_svd(rt, shapes=((440, 330), (165, 220), (400, 156), (88, 81), (20, 12)), graded="plateau"), tol=1e-11)
+    KC.assert_small(KC.case_qr_svd(rt, shapes=((88, 81), (20, 12)), coop_min_dim=1, graded="plateau", noise_floor=1.0), tol=1e-11)
+
+
 def test_qr_svd_tall_panel_in_workspace(rt):
     """unfoldings with more rows than a shared-memory reflector panel holds keep the panel in the workspace"""
     KC.assert_small(KC.case_qr_svd(rt, shapes=((4100, 5), (4, 3900), (6000, 40))), tol=1e-11)

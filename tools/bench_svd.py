@@ -21,6 +21,15 @@ def graded(M, N, decades, rng):
     return (U * np.logspace(0, -decades, K)) @ V.T
 
 
+def plateau(M, N, rng):
+    """the spectrum traced from the maxcut_13 sweep: a third decaying over 9 decades, the rest rounding noise"""
+    K = min(M, N)
+    U, _ = np.linalg.qr(rng.standard_normal((M, K)))
+    V, _ = np.linalg.qr(rng.standard_normal((N, K)))
+    sv = np.concatenate([np.logspace(0, -9, (K + 2) // 3), 1e-14 * rng.uniform(0.1, 1.0, K - (K + 2) // 3)])
+    return 12000.0 * (U * sv) @ V.T
+
+
 def run(rt, a, coop, iters=5):
     M, N = a.shape
     K = min(M, N)
@@ -59,18 +68,19 @@ def main():
     rt = get_runtime()
     rng = np.random.default_rng(0)
     shapes = [(16, 12), (32, 24), (64, 48), (88, 66), (136, 81), (296, 102), (102, 296), (220, 165), (165, 220), (440, 330),
-              (330, 440), (24, 440)]
+              (330, 440), (400, 156), (208, 96), (24, 440)]
     if len(sys.argv) > 1:
         shapes = [tuple(int(v) for v in s.split("x")) for s in sys.argv[1:]]
     out = []
     for (M, N) in shapes:
-        a = graded(M, N, 18, rng)
-        for coop in (True, False):
-            if not coop and min(M, N) > 128:
-                continue                    # one CTA per matrix is for small / batched unfoldings
-            rec = run(rt, a, coop)
-            print(json.dumps(rec), flush=True)
-            out.append(rec)
+        for kind, a in (("graded18", graded(M, N, 18, rng)), ("plateau", plateau(M, N, rng))):
+            for coop in (True, False):
+                if not coop and min(M, N) > 128:
+                    continue                    # one CTA per matrix is for small / batched unfoldings
+                rec = run(rt, a, coop)
+                rec["spectrum"] = kind
+                print(json.dumps(rec), flush=True)
+                out.append(rec)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "bench_svd.jsonl"), "w") as f:
         for rec in out:
