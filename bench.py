@@ -332,11 +332,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    clocks = Clocks(local_rank)
+    clocks.start()                 # sampler runs through the warm-up too (its first NVML queries are slow) ...
     for _ in range(args.warmup):
         device_pass()
-    clocks = Clocks(local_rank)
-    clocks.start()
     barrier()
+    clocks.samples.clear()         # ... but only samples of the timed region are reported
+    clocks.reasons.clear()
     times, launches = [], 0
     for _ in range(args.steps):
         t, nl, solvers, outs = device_pass()
