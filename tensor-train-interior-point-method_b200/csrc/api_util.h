@@ -44,4 +44,16 @@ int mv_big(const MvTerm* t, int nterms, int l, int L, int r, int R, int nm, int 
            long x_rs, long x_ns, long x_batch, double* y, long y_bs, long y_rs, long y_ns, long y_batch, double y_scale,
            const double* sub, double sub_scale, double* sumsq, int nbatch, tt_stream_t st);
 
+// large-rank path of K2 (cgemm.cu)
+struct PhiTermLite {
+    const double* Phi;
+    const double* A;
+    double* out;
+    int as_[4];
+    int s, S;
+};
+bool phi_big_wanted(const PhiTermLite* t, int nterms, int forward, int ul, int uL, int vr, int vR, int nm);
+int phi_big(const PhiTermLite* t, int nterms, int forward, const double* U, int ul, int uL, const double* V, int vr, int vR,
+            int nm, tt_stream_t st);
+
 }  // namespace ttipm

@@ -250,6 +250,122 @@ int mv_big(const MvTerm* t, int nterms, int l, int L, int r, int R, int nm, int 
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K2 (interface update, reference src/tt_als.py:252-257) at large ranks: the same three-launch scheme.
+//   forward : T1[l,s,N,R'] = Phi[l,s,r] V[r,N,R'];  T2[l,M,S,R'] = A[s,M,N,S] T1[l,s,N,R'] (batched over l);
+//             out[L',S,R'] = U[l,M,L'] T2[l,M,S,R']
+//   backward: T1[L,S,r,N] = Phi[L,S,R] V[r,N,R];    T2[L,s,M,r]  = A[s,M,N,S] T1[L,S,r,N]  (batched over L);
+//             out[l,s,r]   = U[l,M,L] T2[L,s,M,r]
+// ---------------------------------------------------------------------------------------------------------------
+static void cg_clear(CgProb& pr) {
+    pr.c_batch = 0; pr.c_scale = 1.0; pr.sub = nullptr; pr.sub_scale = 0.0; pr.sumsq = nullptr; pr.sumsq_batch = 0;
+    pr.sumsq_slots = 0; pr.ksplit = 1; pr.nseg = 1;
+}
+
+bool phi_big_wanted(const PhiTermLite* t, int nterms, int forward, int ul, int uL, int vr, int vR, int nm) {
+    if (nterms < 1 || nterms > CG_MAX_PROBS) return false;
+    double flops = 0.0;
+    for (int q = 0; q < nterms; ++q) {
+        const double s = t[q].s, S = t[q].S;
+        flops += forward ? 2.0 * ul * s * vr * nm * vR + 2.0 * ul * vR * s * nm * nm * S + 2.0 * ul * nm * uL * S * vR
+                         : 2.0 * uL * S * vR * nm * vr + 2.0 * uL * vr * S * nm * nm * s + 2.0 * uL * nm * ul * s * vr;
+    }
+    return flops >= g_big_min_flops;
+}
+
+int phi_big(const PhiTermLite* t, int nterms, int forward, const double* U, int ul, int uL, const double* V, int vr, int vR,
+            int nm, tt_stream_t st) {
+    DevInfo di = dev_info();
+    std::vector<long> o1(nterms), o2(nterms);
+    long total = 0;
+    for (int q = 0; q < nterms; ++q) {
+        const long s = t[q].s, S = t[q].S;
+        o1[q] = total; total += forward ? (long)ul * s * nm * vR : (long)uL * S * vr * nm;
+        o2[q] = total; total += forward ? (long)ul * nm * S * vR : (long)uL * s * nm * vr;
+    }
+    if (!fits_int(total)) return fail(1, "phi_update: intermediates exceed int addressing");
+    double* ws = (double*)scratch_alloc(sizeof(double) * (size_t)total, st);
+    if (!ws) return fail(5, "phi_update: cannot allocate %ld doubles of scratch", total);
+    int rc = 0;
+    {   // ---- stage 1: Phi (rows (l,s) | (L,S)) times V ----
+        CgParams p;
+        p.nprob = nterms; p.nbatch = 1;
+        for (int q = 0; q < nterms; ++q) {
+            const int s = t[q].s, S = t[q].S;
+            CgSeg& g = p.seg[q];
+            CgProb& pr = p.prob[q];
+            cg_clear(pr);
+            pr.seg0 = q;
+            g.A = t[q].Phi; g.a_batch = 0; g.b_batch = 0; g.B = V; g.a_kfast = 1;
+            g.aK = AxisMap{TT_AX_BIG, 0, 1};
+            if (forward) {
+                g.aM = AxisMap{TT_AX_BIG, 0, vr}; g.K = vr;
+                g.bK = AxisMap{TT_AX_BIG, 0, nm * vR}; g.bN = AxisMap{TT_AX_BIG, 0, 1}; g.b_kfast = 0;
+                pr.M = ul * s; pr.N = nm * vR;
+            } else {
+                g.aM = AxisMap{TT_AX_BIG, 0, vR}; g.K = vR;
+                g.bK = AxisMap{TT_AX_BIG, 0, 1}; g.bN = AxisMap{TT_AX_BIG, 0, vR}; g.b_kfast = 1;
+                pr.M = uL * S; pr.N = vr * nm;
+            }
+            pr.C = ws + o1[q]; pr.cM = AxisMap{TT_AX_BIG, 0, pr.N}; pr.cN = AxisMap{TT_AX_BIG, 0, 1};
+        }
+        rc = cg_run(p, di.sms, st);
+    }
+    if (!rc) {   // ---- stage 2: operator core, batched over the leading interface index ----
+        CgParams p;
+        p.nprob = nterms; p.nbatch = forward ? ul : uL;
+        for (int q = 0; q < nterms; ++q) {
+            const int s = t[q].s, S = t[q].S;
+            const int* as_ = t[q].as_;
+            CgSeg& g = p.seg[q];
+            CgProb& pr = p.prob[q];
+            cg_clear(pr);
+            pr.seg0 = q;
+            g.A = t[q].A; g.a_batch = 0; g.B = ws + o1[q];
+            if (forward) {
+                // A(m = (M,S), k = (s,N)), B(k = (s,N), n = R') = T1[l][k][R']
+                g.aM = AxisMap{S, as_[1], as_[3]}; g.aK = AxisMap{nm, as_[0], as_[2]}; g.a_kfast = 0; g.K = s * nm;
+                g.bK = AxisMap{TT_AX_BIG, 0, vR}; g.bN = AxisMap{TT_AX_BIG, 0, 1}; g.b_kfast = 0; g.b_batch = (long)s * nm * vR;
+                pr.M = nm * S; pr.N = vR; pr.c_batch = (long)nm * S * vR;
+            } else {
+                // A(m = (s,M), k = (S,N)), B(k = (S,N), n = r) = T1[L][S][r][N]
+                g.aM = AxisMap{nm, as_[0], as_[1]}; g.aK = AxisMap{nm, as_[3], as_[2]}; g.a_kfast = 1; g.K = S * nm;
+                g.bK = AxisMap{nm, vr * nm, 1}; g.bN = AxisMap{TT_AX_BIG, 0, nm}; g.b_kfast = 1; g.b_batch = (long)S * vr * nm;
+                pr.M = s * nm; pr.N = vr; pr.c_batch = (long)s * nm * vr;
+            }
+            pr.C = ws + o2[q]; pr.cM = AxisMap{TT_AX_BIG, 0, pr.N}; pr.cN = AxisMap{TT_AX_BIG, 0, 1};
+        }
+        rc = cg_run(p, di.sms, st);
+    }
+    if (!rc) {   // ---- stage 3: the left core ----
+        CgParams p;
+        p.nprob = nterms; p.nbatch = 1;
+        for (int q = 0; q < nterms; ++q) {
+            const int s = t[q].s, S = t[q].S;
+            CgSeg& g = p.seg[q];
+            CgProb& pr = p.prob[q];
+            cg_clear(pr);
+            pr.seg0 = q;
+            g.A = U; g.a_batch = 0; g.B = ws + o2[q]; g.b_batch = 0;
+            if (forward) {
+                // A(m = L', k = (l,M)) = U[k * uL + m];  B(k, n = (S,R')) = T2[k][n]
+                g.aM = AxisMap{TT_AX_BIG, 0, 1}; g.aK = AxisMap{TT_AX_BIG, 0, uL}; g.a_kfast = 0; g.K = ul * nm;
+                g.bK = AxisMap{TT_AX_BIG, 0, S * vR}; g.bN = AxisMap{TT_AX_BIG, 0, 1}; g.b_kfast = 0;
+                pr.M = uL; pr.N = S * vR;
+            } else {
+                // A(m = l, k = (M,L)) = U[m * nm * uL + k];  B(k = (M,L), n = (s,r)) = T2[L][s][M][r]
+                g.aM = AxisMap{TT_AX_BIG, 0, nm * uL}; g.aK = AxisMap{TT_AX_BIG, 0, 1}; g.a_kfast = 1; g.K = nm * uL;
+                g.bK = AxisMap{uL, vr, s * nm * vr}; g.bN = AxisMap{vr, nm * vr, 1}; g.b_kfast = 0;
+                pr.M = ul; pr.N = s * vr;
+            }
+            pr.C = t[q].out; pr.cM = AxisMap{TT_AX_BIG, 0, pr.N}; pr.cN = AxisMap{TT_AX_BIG, 0, 1};
+        }
+        rc = cg_run(p, di.sms, st);
+    }
+    scratch_free(ws, st);
+    return rc;
+}
+
 }  // namespace ttipm
 
 using namespace ttipm;

@@ -226,6 +226,16 @@ extern "C" int ttipm_phi_update(const ttipm_phi_term* terms, int nterms, int for
         if (terms[i].S > Smax) Smax = terms[i].S;
     }
     p.U = U; p.V = V; p.ul = ul; p.uL = uL; p.vr = vr; p.vR = vR; p.nm = nmode; p.forward = forward;
+    // large interfaces: three grouped contraction-GEMM launches (cgemm.cu); also the fallback when the fused kernel's
+    // intermediates do not fit shared memory
+    PhiTermLite lite[TTIPM_MAX_TERMS];
+    for (int i = 0; i < nterms; ++i) {
+        lite[i].Phi = p.t[i].Phi; lite[i].A = p.t[i].A; lite[i].out = p.t[i].out;
+        for (int j = 0; j < 4; ++j) lite[i].as_[j] = p.t[i].as_[j];
+        lite[i].s = p.t[i].s; lite[i].S = p.t[i].S;
+    }
+    if (phi_big_wanted(lite, nterms, forward, ul, uL, vr, vR, nmode))
+        return phi_big(lite, nterms, forward, U, ul, uL, V, vr, vR, nmode, (tt_stream_t)stream);
     DevInfo di = dev_info();
     const int free_dim = forward ? vR : vr;
     int tile = (nterms * free_dim + 2 * di.sms - 1) / (2 * di.sms);
@@ -251,7 +261,7 @@ extern "C" int ttipm_phi_update(const ttipm_phi_term* terms, int nterms, int for
             return launch_kernel("k_phi_update", k_phi_update, dim3(nterms * p.ntiles), dim3(block_threads()), bytes,
                                  (tt_stream_t)stream, false, p);
         }
-        if (tile == 1) return fail(4, "phi_update: shapes need %d B shared memory (> %d)", bytes, di.smem_optin);
+        if (tile == 1) return phi_big(lite, nterms, forward, U, ul, uL, V, vr, vR, nmode, (tt_stream_t)stream);
         tile /= 2;
     }
 }

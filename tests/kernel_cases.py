@@ -130,6 +130,36 @@ def case_phi(rt, case):
     return errs
 
 
+def case_phi_big(rt, case=None, shape=None):
+    """K2 through the grouped contraction-GEMM path (csrc/cgemm.cu, three launches) forced onto the fixture cases, or on a
+    random interface set of the given shape (l, L, r, R, {key: (s, S)}) against the oracle's einsum restatement
+    (reference src/tt_als.py:252-257)."""
+    old = rt.lib.ttipm_matvec_big_min_flops(0.0)
+    try:
+        if case is not None:
+            return case_phi(rt, case)
+        l, L, r, R, ranks = shape
+        rng = np.random.default_rng(9)
+        n = 4
+        A = {k: rng.standard_normal((s, n, n, S)) for k, (s, S) in ranks.items()}
+        U, V = rng.standard_normal((l, n, L)), rng.standard_normal((r, n, R))
+        errs = {}
+        keys = list(A.keys())
+        up = rt.to_device
+        for fwd in (True, False):
+            phis = {k: rng.standard_normal((l, s, r) if fwd else (L, S, R)) for k, (s, S) in ranks.items()}
+            outs = K.phi_update([up(phis[k]) for k in keys], [up(A[k]) for k in keys], up(U), up(V), fwd, rt=rt)
+            ref = [(O.phi_fwd if fwd else O.phi_bck)(phis[k], U, A[k], V) for k in keys]
+            errs["phi_big_fwd" if fwd else "phi_big_bck"] = max(rel(rt.to_host(o), w) for o, w in zip(outs, ref))
+            At = up(A[keys[0]]).permute(0, 2, 1, 3)             # m <-> n swapped core through strides only
+            o = K.phi_update([up(phis[keys[0]])], [At], up(U), up(V), fwd, rt=rt)[0]
+            w = (O.phi_fwd if fwd else O.phi_bck)(phis[keys[0]], U, A[keys[0]].transpose(0, 2, 1, 3), V)
+            errs["phi_big_T_fwd" if fwd else "phi_big_T_bck"] = rel(rt.to_host(o), w)
+        return errs
+    finally:
+        rt.lib.ttipm_matvec_big_min_flops(old)
+
+
 def case_rhs(rt, case):
     c = load_blp_case(case)
     z, p, nb = c["z"], c["p"], c["nb"]

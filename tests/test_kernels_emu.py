@@ -50,6 +50,17 @@ def test_phi(rt, case):
 
 
 @pytest.mark.parametrize("case", CASES)
+def test_phi_grouped_gemm_path(rt, case):
+    KC.assert_small(KC.case_phi_big(rt, case))
+
+
+def test_phi_grouped_gemm_random(rt):
+    ranks = {(0, 0): (2, 3), (0, 1): (3, 2), (2, 2): (4, 2)}
+    KC.assert_small(KC.case_phi_big(rt, shape=(5, 6, 7, 3, ranks)))
+    KC.assert_small(KC.case_phi_big(rt, shape=(2, 9, 3, 8, ranks)))      # z-interface like: thin left core
+
+
+@pytest.mark.parametrize("case", CASES)
 def test_rhs(rt, case):
     KC.assert_small(KC.case_rhs(rt, case))
 

@@ -25,6 +25,18 @@ def test_phi(rt, case):
 
 
 @pytest.mark.parametrize("case", CASES)
+def test_phi_grouped_gemm_path(rt, case):
+    KC.assert_small(KC.case_phi_big(rt, case))
+
+
+@pytest.mark.parametrize("l,L,r,R,s", [(55, 55, 55, 55, 5), (2, 44, 29, 44, 10), (130, 97, 130, 97, 17), (128, 128, 128, 128, 32)])
+def test_phi_grouped_gemm_vs_oracle(rt, l, L, r, R, s):
+    """K2 on large / ragged interfaces; (128, 128, s = 32) is a shape the fused kernel cannot hold in shared memory"""
+    ranks = {(0, 0): (2, 3), (0, 1): (s, s - 1), (2, 1): (s, s), (2, 2): (s - 1, s)}
+    KC.assert_small(KC.case_phi_big(rt, shape=(l, L, r, R, ranks)))
+
+
+@pytest.mark.parametrize("case", CASES)
 def test_rhs(rt, case):
     KC.assert_small(KC.case_rhs(rt, case))
 
