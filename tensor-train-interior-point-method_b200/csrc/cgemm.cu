@@ -144,6 +144,16 @@ static int cg_run(CgParams& p, int sms, tt_stream_t st) {
     return rc;
 }
 
+bool mv_big_possible(int nterms, int l, int L, int nm, int nb_out) {
+    if (nterms < 1 || nterms > CG_MAX_PROBS || nb_out > CG_MAX_PROBS) return false;
+#ifdef TTIPM_EMU
+    const int mt = 16;
+#else
+    const int mt = 64;
+#endif
+    return (long)((l + mt - 1) / mt) * ((nm * L + mt - 1) / mt) <= L;
+}
+
 bool mv_big_wanted(const MvTerm* t, int nterms, int l, int L, int r, int R, int nm, int nb_out, int nbatch) {
     if (nterms < 1 || nterms > CG_MAX_PROBS || nb_out > CG_MAX_PROBS) return false;
     double flops = 0.0;

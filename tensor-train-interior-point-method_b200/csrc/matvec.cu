@@ -142,9 +142,15 @@ extern "C" int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, in
                       y, y_block_stride, y_row_stride, y_mode_stride, y_batch_stride, y_scale, sub, sub_scale, sumsq, nbatch,
                       (tt_stream_t)stream);
     DevInfo di = dev_info();
-    if (mv_plan(p.g, l, L, r, R, nmode, smax, Smax, nb_out, (di.sms * 2 + nbatch - 1) / nbatch, di.smem_optin))
+    if (mv_plan(p.g, l, L, r, R, nmode, smax, Smax, nb_out, (di.sms * 2 + nbatch - 1) / nbatch, di.smem_optin)) {
+        // the fused kernel's intermediates do not fit shared memory: the grouped-GEMM path has no such limit
+        if (mv_big_possible(nterms, l, L, nmode, nb_out))
+            return mv_big(p.t, nterms, l, L, r, R, nmode, nb_out, x, x_block_stride, x_row_stride, x_mode_stride,
+                          x_batch_stride, y, y_block_stride, y_row_stride, y_mode_stride, y_batch_stride, y_scale, sub,
+                          sub_scale, sumsq, nbatch, (tt_stream_t)stream);
         return fail(4, "block_matvec: shape l=%d L=%d r=%d R=%d s=%d S=%d needs %d B shared memory (> %d)", l, L, r,
                     R, smax, Smax, p.g.smem_bytes, di.smem_optin);
+    }
     p.x = x; p.x_bs = x_block_stride; p.x_rs = x_row_stride; p.x_ns = x_mode_stride; p.x_batch = x_batch_stride;
     p.y = y; p.y_bs = y_block_stride; p.y_rs = y_row_stride; p.y_ns = y_mode_stride; p.y_batch = y_batch_stride;
     p.y_scale = y_scale; p.sub_scale = sub_scale;
