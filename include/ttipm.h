@@ -129,9 +129,6 @@ int ttipm_gemm(int M, int N, int K, double alpha, const double* A, int64_t a_rs,
  * the wrappers).  info (device, 6 doubles, may be NULL) = its, matvecs, reason, cycles, residual
  * estimate, grid size; reason: 1 rtol, 2 atol, 3 max_it, -1 dtol, -2 breakdown, -3 null pivot, -4 nan.
  * grid_hint = 0 lets the library choose the number of CTAs. */
-/* Single-CTA solves stage every operand of the reduced operator in shared memory once (1, default); 0 reads them from
- * global memory in every matvec (tuning / test hook).  Returns the previous setting; a negative argument only queries. */
-int ttipm_lgmres_stage_operands(int on);
 int64_t ttipm_lgmres_workspace(int ineq, int r, int R, int nmode, int restart, int augment);
 int ttipm_local_lgmres(int ineq, const ttipm_term* K00, const ttipm_term* K01, const ttipm_term* K21,
                        const ttipm_term* K22, const ttipm_term* K31, const ttipm_term* K33, const double* inv_I,

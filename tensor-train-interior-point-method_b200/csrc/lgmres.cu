@@ -44,23 +44,15 @@ struct LgParams {
     int mode;
     int ch;                   // chunk length per CTA
     int oW, oH, oScr;         // CGS shared-memory offsets (doubles)
-    // single-CTA solves (tiny local systems, the small / medium regime): every operand of the reduced operator and the
-    // vector being multiplied are staged in shared memory once, so the 15-21 dependent GEMM stages of one matvec read
-    // shared memory (~30 cycles) instead of L2 (~700 cycles)
-    int stage;                // 1: stage operands (grid of one CTA and enough shared memory)
-    int oStage;               // offset of the staging area (doubles): [term copies][operand data][vector nv]
+    int oHess;                // CTA 0: Givens cosines / sines, rotated rhs, working Hessenberg column, back-substitution
+                              // vector in shared memory (5 x (max_k + 2) doubles, outside the matvec / CGS scratch)
 };
-
-#define LG_STAGE_TERM_DOUBLES ((int)((12 * sizeof(MvTerm) + 7) / 8))
 
 struct LgCtx {
     const LgParams& p;
     double* smem;
     unsigned epoch;
-    const MvTerm* tA;         // phase A / B term lists: the kernel parameters, or their shared-memory staged copies
-    const MvTerm* tB;
-    double* xs;               // staged input vector (nullptr when not staging)
-    TT_DEVM LgCtx(const LgParams& pp, double* s) : p(pp), smem(s), epoch(0), tA(pp.tA), tB(pp.tB), xs(nullptr) {}
+    TT_DEVM LgCtx(const LgParams& pp, double* s) : p(pp), smem(s), epoch(0) {}
     TT_DEVM void sync() { grid_sync(p.barrier, epoch); }
 };
 
@@ -96,58 +88,11 @@ TT_DEV void lg_item(LgCtx& c, const MvTerm* terms, int nterms, int slot, int til
 TT_DEV void lg_apply(LgCtx& c, const double* src, double* dst) {
     const LgParams& p = c.p;
     const int nt = p.g.ntiles;
-    if (c.xs) {                        // single CTA: the vector being multiplied goes to shared memory once
-        __syncthreads();
-        for (int e = threadIdx.x; e < p.nv; e += blockDim.x) c.xs[e] = src[e];
-        __syncthreads();
-        src = c.xs;
-    }
     for (int it = blockIdx.x; it < p.nslotA * nt; it += gridDim.x)
-        lg_item(c, c.tA, p.nA, p.slotA[it / nt], it % nt, src, dst);
+        lg_item(c, p.tA, p.nA, p.slotA[it / nt], it % nt, src, dst);
     c.sync();
-    for (int it = blockIdx.x; it < nt; it += gridDim.x) lg_item(c, c.tB, p.nB, 1, it, src, dst);
+    for (int it = blockIdx.x; it < nt; it += gridDim.x) lg_item(c, p.tB, p.nB, 1, it, src, dst);
     c.sync();
-}
-
-// copy the logical (d0, d1, d2[, d3]) tensor addressed by `strides` to a contiguous block of shared memory
-TT_DEV void lg_stage_tensor(double* dst, const double* src, int d0, int d1, int d2, int d3, const int* st) {
-    const int n = d0 * d1 * d2 * d3;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int t = i;
-        const int i3 = t % d3; t /= d3;
-        const int i2 = t % d2; t /= d2;
-        const int i1 = t % d1; t /= d1;
-        dst[i] = src[t * st[0] + i1 * st[1] + i2 * st[2] + (d3 > 1 ? i3 * st[3] : 0)];
-    }
-}
-
-// stage every operand of the reduced operator (single-CTA solves); returns after a block barrier
-TT_DEV void lg_stage_operands(LgCtx& c) {
-    const LgParams& p = c.p;
-    double* base = c.smem + p.oStage;
-    MvTerm* tl = (MvTerm*)base;
-    double* data = base + LG_STAGE_TERM_DOUBLES;
-    const int r = p.g.r, R = p.g.R, nm = p.g.nm;
-    int off = 0;
-    for (int q = 0; q < p.nA + p.nB; ++q) {
-        const MvTerm& t = q < p.nA ? p.tA[q] : p.tB[q - p.nA];
-        const int n1 = r * t.s * r, nA = t.s * nm * nm * t.S, n2 = R * t.S * R;
-        lg_stage_tensor(data + off, t.P1, r, t.s, r, 1, t.p1s);
-        lg_stage_tensor(data + off + n1, t.A, t.s, nm, nm, t.S, t.as_);
-        lg_stage_tensor(data + off + n1 + nA, t.P2, R, t.S, R, 1, t.p2s);
-        if (threadIdx.x == 0) {
-            MvTerm u = t;
-            u.P1 = data + off; u.p1s[0] = t.s * r; u.p1s[1] = r; u.p1s[2] = 1;
-            u.A = data + off + n1; u.as_[0] = nm * nm * t.S; u.as_[1] = nm * t.S; u.as_[2] = t.S; u.as_[3] = 1;
-            u.P2 = data + off + n1 + nA; u.p2s[0] = t.S * R; u.p2s[1] = R; u.p2s[2] = 1;
-            tl[q] = u;
-        }
-        off += n1 + nA + n2;
-    }
-    c.tA = tl;
-    c.tB = tl + p.nA;
-    c.xs = data + off;
-    __syncthreads();
 }
 
 TT_DEV double lg_sum_partials(const LgParams& p, int col) {
@@ -178,13 +123,17 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_lgmres(const LgParams p) {
     double* hS = smem + p.oH;
     double* scr = smem + p.oScr;
     double* mypart = p.part + (long)blockIdx.x * (p.max_k + 3);
-    double* grs = p.small_;
-    double* cc = grs + (p.max_k + 2);
-    double* ss = cc + (p.max_k + 1);
-    double* nrs = ss + (p.max_k + 1);
+    double* nrs = p.small_ + (p.max_k + 2) + 2 * (p.max_k + 1);
     double* avec = nrs + (p.max_k + 2);
+    // the small dense recurrences of GMRES run on CTA 0 out of shared memory (one warp; the serial Givens chain on
+    // lane 0): in global memory every dependent load of the chain costs an L2 round trip
+    double* cc = smem + p.oHess;
+    double* ss = cc + (p.max_k + 2);
+    double* grs = ss + (p.max_k + 2);
+    double* colS = grs + (p.max_k + 2);
+    double* tS = colS + (p.max_k + 2);
     const bool lead = blockIdx.x == 0 && tid == 0;
-    if (p.stage) lg_stage_operands(c);
+    const bool lead_warp = blockIdx.x == 0 && wid == 0;
 
     if (p.mode == LG_APPLY) {
         lg_apply(c, p.b, p.x);
@@ -224,6 +173,7 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_lgmres(const LgParams p) {
             grs[0] = res_norm;
             p.ctrl_d[1] = res_norm;
         }
+        __syncwarp();
         if (res == 0.0) {
             reason = R_ATOL;
             break;
@@ -291,36 +241,40 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_lgmres(const LgParams p) {
                 for (int e = e0 + tid; e < e1; e += nth) Vn[e] = wS[e - e0];
                 hapend = true;
             }
-            if (lead) {
+            if (lead_warp) {
                 double* col = p.hh + (long)loc_it * ldh;
                 double* hcol = p.hes + (long)loc_it * ldh;
-                for (int i = 0; i <= loc_it; ++i) {
-                    col[i] = hS[i];
-                    hcol[i] = hS[i];
+                for (int i = lane; i <= loc_it + 1; i += 32) {
+                    const double v = i <= loc_it ? hS[i] : tt;
+                    colS[i] = v;
+                    hcol[i] = v;
                 }
-                col[loc_it + 1] = tt;
-                hcol[loc_it + 1] = tt;
-                for (int j = 0; j < loc_it; ++j) {
-                    const double t0 = col[j];
-                    col[j] = cc[j] * t0 + ss[j] * col[j + 1];
-                    col[j + 1] = cc[j] * col[j + 1] - ss[j] * t0;
-                }
-                double newres = 0.0;
-                if (!hapend) {
-                    const double t0 = sqrt(col[loc_it] * col[loc_it] + col[loc_it + 1] * col[loc_it + 1]);
-                    if (t0 == 0.0) {
-                        p.ctrl_i[0] = 1;
-                    } else {
-                        cc[loc_it] = col[loc_it] / t0;
-                        ss[loc_it] = col[loc_it + 1] / t0;
-                        grs[loc_it + 1] = -(ss[loc_it] * grs[loc_it]);
-                        grs[loc_it] = cc[loc_it] * grs[loc_it];
-                        col[loc_it] = cc[loc_it] * col[loc_it] + ss[loc_it] * col[loc_it + 1];
-                        newres = fabs(grs[loc_it + 1]);
+                __syncwarp();
+                if (lane == 0) {
+                    for (int j = 0; j < loc_it; ++j) {
+                        const double t0 = colS[j];
+                        colS[j] = cc[j] * t0 + ss[j] * colS[j + 1];
+                        colS[j + 1] = cc[j] * colS[j + 1] - ss[j] * t0;
                     }
+                    double newres = 0.0;
+                    if (!hapend) {
+                        const double t0 = sqrt(colS[loc_it] * colS[loc_it] + colS[loc_it + 1] * colS[loc_it + 1]);
+                        if (t0 == 0.0) {
+                            p.ctrl_i[0] = 1;
+                        } else {
+                            cc[loc_it] = colS[loc_it] / t0;
+                            ss[loc_it] = colS[loc_it + 1] / t0;
+                            grs[loc_it + 1] = -(ss[loc_it] * grs[loc_it]);
+                            grs[loc_it] = cc[loc_it] * grs[loc_it];
+                            colS[loc_it] = cc[loc_it] * colS[loc_it] + ss[loc_it] * colS[loc_it + 1];
+                            newres = fabs(grs[loc_it + 1]);
+                        }
+                    }
+                    p.ctrl_d[0] = newres;
+                    p.ctrl_d[1] = grs[loc_it + 1];
                 }
-                p.ctrl_d[0] = newres;
-                p.ctrl_d[1] = grs[loc_it + 1];
+                __syncwarp();
+                for (int i = lane; i <= loc_it + 1; i += 32) col[i] = colS[i];
             }
             c.sync();
             if (ld_cg_i(&p.ctrl_i[0]) != 0) {
@@ -348,13 +302,17 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_lgmres(const LgParams p) {
                 n_arn = it_arnoldi;
                 n_aug = it + 1 - it_arnoldi;
             }
-            if (lead) {
-                const double d = p.hh[(long)it * ldh + it];
-                nrs[it] = d != 0.0 ? grs[it] / d : 0.0;
-                for (int k = it - 1; k >= 0; --k) {
-                    double t0 = grs[k];
-                    for (int j = k + 1; j <= it; ++j) t0 -= p.hh[(long)j * ldh + k] * nrs[j];
-                    nrs[k] = t0 / p.hh[(long)k * ldh + k];
+            if (lead_warp) {
+                // back-substitution R y = g, column oriented: one division per step on the diagonal, the update of the
+                // remaining right-hand side spread over the lanes (columns of hh are contiguous)
+                for (int i = lane; i <= it; i += 32) tS[i] = grs[i];
+                __syncwarp();
+                for (int k = it; k >= 0; --k) {
+                    const double d = p.hh[(long)k * ldh + k];
+                    const double yk = (k == it && d == 0.0) ? 0.0 : tS[k] / d;
+                    if (lane == 0) nrs[k] = yk;
+                    for (int i = lane; i < k; i += 32) tS[i] -= p.hh[(long)k * ldh + i] * yk;
+                    __syncwarp();
                 }
             }
             c.sync();
@@ -396,11 +354,12 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_lgmres(const LgParams p) {
                 s2 = block_sum(s2, scr);
                 if (tid == 0) mypart[0] = s2;
             }
-            if (lead) {
-                for (int i = 0; i <= it_total; ++i) avec[i] = 0.0;
-                for (int ii = 0; ii < it_total; ++ii) {
-                    const int hi = imin(ii + 2, it_total + 1);
-                    for (int jj = 0; jj < hi; ++jj) avec[jj] += p.hes[(long)ii * ldh + jj] * nrs[ii];
+            if (lead_warp) {
+                // avec = H y (the un-rotated Hessenberg matrix times the cycle's solution), one output entry per lane
+                for (int jj = lane; jj <= it_total; jj += 32) {
+                    double a = 0.0;
+                    for (int ii = imax(0, jj - 1); ii < it_total; ++ii) a += p.hes[(long)ii * ldh + jj] * nrs[ii];
+                    avec[jj] = a;
                 }
             }
             c.sync();
@@ -432,8 +391,6 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_lgmres(const LgParams p) {
         p.ctrl_d[2] = res;
     }
 }
-
-static int g_stage_enabled = 1;
 
 static int lg_setup(LgParams& p, int ineq, const ttipm_term* K00, const ttipm_term* K01, const ttipm_term* K21,
                     const ttipm_term* K22, const ttipm_term* K31, const ttipm_term* K33, const double* inv_I, int r,
@@ -493,19 +450,8 @@ static int lg_setup(LgParams& p, int ineq, const ttipm_term* K00, const ttipm_te
         p.oScr = p.oH + max_k + 4;
         const int cgs_bytes = (p.oScr + 40) * 8;
         int bytes = imax(p.g.smem_bytes, cgs_bytes);
-        p.stage = 0;
-        p.oStage = 0;
-        if (G == 1 && g_stage_enabled) {
-            long data = LG_STAGE_TERM_DOUBLES + p.nv;
-            for (int i = 0; i < p.nA; ++i) data += (long)r * p.tA[i].s * r + (long)p.tA[i].s * nmode * nmode * p.tA[i].S + (long)R * p.tA[i].S * R;
-            for (int i = 0; i < p.nB; ++i) data += (long)r * p.tB[i].s * r + (long)p.tB[i].s * nmode * nmode * p.tB[i].S + (long)R * p.tB[i].S * R;
-            const long o = (bytes + 15) / 16 * 2;
-            if ((o + data) * 8 <= di.smem_optin) {
-                p.stage = 1;
-                p.oStage = (int)o;
-                bytes = (int)((o + data) * 8);
-            }
-        }
+        p.oHess = (bytes + 15) / 16 * 2;
+        bytes = (p.oHess + 5 * (max_k + 2)) * 8;
         if (bytes <= di.smem_optin) {
             *grid_out = G;
             *smem_out = bytes;
@@ -537,12 +483,6 @@ static int launch_info_copy(const int* ci, const double* cd, double* out, int gr
 }  // namespace ttipm
 
 using namespace ttipm;
-
-extern "C" int ttipm_lgmres_stage_operands(int on) {
-    const int old = g_stage_enabled;
-    if (on >= 0) g_stage_enabled = on ? 1 : 0;
-    return old;
-}
 
 extern "C" int64_t ttipm_lgmres_workspace(int ineq, int r, int R, int nmode, int restart, int augment) {
     const int64_t nv = (int64_t)(ineq ? 3 : 2) * r * nmode * R, m = (int64_t)r * nmode * R;
