@@ -44,15 +44,25 @@ struct LgParams {
     int mode;
     int ch;                   // chunk length per CTA
     int oW, oH, oScr;         // CGS shared-memory offsets (doubles)
+    // single-CTA solves (tiny local systems, the small / medium regime): every operand of the reduced operator and the
+    // vector being multiplied are staged in shared memory once per solve; together with the scalar small-block stages
+    // of matvec.cuh a matvec then never waits for L2 (each of its ~15 dependent stages otherwise pays 1-4 L2 round trips)
+    int stage;                // 1: stage operands (grid of one CTA and enough shared memory)
+    int oStage;               // offset of the staging area (doubles): [term copies][operand data][vector nv]
     int oHess;                // CTA 0: Givens cosines / sines, rotated rhs, working Hessenberg column, back-substitution
                               // vector in shared memory (5 x (max_k + 2) doubles, outside the matvec / CGS scratch)
 };
+
+#define LG_STAGE_TERM_DOUBLES ((int)((12 * sizeof(MvTerm) + 7) / 8))
 
 struct LgCtx {
     const LgParams& p;
     double* smem;
     unsigned epoch;
-    TT_DEVM LgCtx(const LgParams& pp, double* s) : p(pp), smem(s), epoch(0) {}
+    const MvTerm* tA;         // phase A / B term lists: the kernel parameters, or their shared-memory staged copies
+    const MvTerm* tB;
+    double* xs;               // staged input vector (nullptr when not staging)
+    TT_DEVM LgCtx(const LgParams& pp, double* s) : p(pp), smem(s), epoch(0), tA(pp.tA), tB(pp.tB), xs(nullptr) {}
     TT_DEVM void sync() { grid_sync(p.barrier, epoch); }
 };
 
@@ -88,11 +98,58 @@ TT_DEV void lg_item(LgCtx& c, const MvTerm* terms, int nterms, int slot, int til
 TT_DEV void lg_apply(LgCtx& c, const double* src, double* dst) {
     const LgParams& p = c.p;
     const int nt = p.g.ntiles;
+    if (c.xs) {                        // single CTA: the vector being multiplied goes to shared memory once
+        __syncthreads();
+        for (int e = threadIdx.x; e < p.nv; e += blockDim.x) c.xs[e] = src[e];
+        __syncthreads();
+        src = c.xs;
+    }
     for (int it = blockIdx.x; it < p.nslotA * nt; it += gridDim.x)
-        lg_item(c, p.tA, p.nA, p.slotA[it / nt], it % nt, src, dst);
+        lg_item(c, c.tA, p.nA, p.slotA[it / nt], it % nt, src, dst);
     c.sync();
-    for (int it = blockIdx.x; it < nt; it += gridDim.x) lg_item(c, p.tB, p.nB, 1, it, src, dst);
+    for (int it = blockIdx.x; it < nt; it += gridDim.x) lg_item(c, c.tB, p.nB, 1, it, src, dst);
     c.sync();
+}
+
+// copy the logical (d0, d1, d2[, d3]) tensor addressed by `strides` to a contiguous block of shared memory
+TT_DEV void lg_stage_tensor(double* dst, const double* src, int d0, int d1, int d2, int d3, const int* st) {
+    const int n = d0 * d1 * d2 * d3;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int t = i;
+        const int i3 = t % d3; t /= d3;
+        const int i2 = t % d2; t /= d2;
+        const int i1 = t % d1; t /= d1;
+        dst[i] = src[t * st[0] + i1 * st[1] + i2 * st[2] + (d3 > 1 ? i3 * st[3] : 0)];
+    }
+}
+
+// stage every operand of the reduced operator (single-CTA solves); returns after a block barrier
+TT_DEV void lg_stage_operands(LgCtx& c) {
+    const LgParams& p = c.p;
+    double* base = c.smem + p.oStage;
+    MvTerm* tl = (MvTerm*)base;
+    double* data = base + LG_STAGE_TERM_DOUBLES;
+    const int r = p.g.r, R = p.g.R, nm = p.g.nm;
+    int off = 0;
+    for (int q = 0; q < p.nA + p.nB; ++q) {
+        const MvTerm& t = q < p.nA ? p.tA[q] : p.tB[q - p.nA];
+        const int n1 = r * t.s * r, nA = t.s * nm * nm * t.S, n2 = R * t.S * R;
+        lg_stage_tensor(data + off, t.P1, r, t.s, r, 1, t.p1s);
+        lg_stage_tensor(data + off + n1, t.A, t.s, nm, nm, t.S, t.as_);
+        lg_stage_tensor(data + off + n1 + nA, t.P2, R, t.S, R, 1, t.p2s);
+        if (threadIdx.x == 0) {
+            MvTerm u = t;
+            u.P1 = data + off; u.p1s[0] = t.s * r; u.p1s[1] = r; u.p1s[2] = 1;
+            u.A = data + off + n1; u.as_[0] = nm * nm * t.S; u.as_[1] = nm * t.S; u.as_[2] = t.S; u.as_[3] = 1;
+            u.P2 = data + off + n1 + nA; u.p2s[0] = t.S * R; u.p2s[1] = R; u.p2s[2] = 1;
+            tl[q] = u;
+        }
+        off += n1 + nA + n2;
+    }
+    c.tA = tl;
+    c.tB = tl + p.nA;
+    c.xs = data + off;
+    __syncthreads();
 }
 
 TT_DEV double lg_sum_partials(const LgParams& p, int col) {
@@ -112,7 +169,7 @@ TT_DEV int lg_converged(const LgParams& p, int it, double rn, double& ttol, doub
     return R_NONE;
 }
 
-TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_lgmres(const LgParams p) {
+TT_GLOBAL void __launch_bounds__(512) k_lgmres(const LgParams p) {
     TT_SMEM_DECL(smem_raw);
     double* smem = (double*)smem_raw;
     LgCtx c(p, smem);
@@ -134,6 +191,7 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_lgmres(const LgParams p) {
     double* tS = colS + (p.max_k + 2);
     const bool lead = blockIdx.x == 0 && tid == 0;
     const bool lead_warp = blockIdx.x == 0 && wid == 0;
+    if (p.stage) lg_stage_operands(c);
 
     if (p.mode == LG_APPLY) {
         lg_apply(c, p.b, p.x);
@@ -392,6 +450,8 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_lgmres(const LgParams p) {
     }
 }
 
+static int g_single_cta_threads = 512;
+
 static int lg_setup(LgParams& p, int ineq, const ttipm_term* K00, const ttipm_term* K01, const ttipm_term* K21,
                     const ttipm_term* K22, const ttipm_term* K31, const ttipm_term* K33, const double* inv_I, int r,
                     int R, int nmode, int grid_hint, int* grid_out, int* smem_out, int max_k) {
@@ -452,6 +512,19 @@ static int lg_setup(LgParams& p, int ineq, const ttipm_term* K00, const ttipm_te
         int bytes = imax(p.g.smem_bytes, cgs_bytes);
         p.oHess = (bytes + 15) / 16 * 2;
         bytes = (p.oHess + 5 * (max_k + 2)) * 8;
+        p.stage = 0;
+        p.oStage = 0;
+        if (G == 1) {
+            long data = LG_STAGE_TERM_DOUBLES + p.nv;
+            for (int i = 0; i < p.nA; ++i) data += (long)r * p.tA[i].s * r + (long)p.tA[i].s * nmode * nmode * p.tA[i].S + (long)R * p.tA[i].S * R;
+            for (int i = 0; i < p.nB; ++i) data += (long)r * p.tB[i].s * r + (long)p.tB[i].s * nmode * nmode * p.tB[i].S + (long)R * p.tB[i].S * R;
+            const long o = (bytes + 15) / 16 * 2;
+            if ((o + data) * 8 <= di.smem_optin) {
+                p.stage = 1;
+                p.oStage = (int)o;
+                bytes = (int)((o + data) * 8);
+            }
+        }
         if (bytes <= di.smem_optin) {
             *grid_out = G;
             *smem_out = bytes;
@@ -460,6 +533,17 @@ static int lg_setup(LgParams& p, int ineq, const ttipm_term* K00, const ttipm_te
         if (G >= di.sms) return fail(4, "lgmres: Krylov chunk of %d doubles does not fit in shared memory", p.ch);
         G = imin(di.sms, G * 2);
     }
+}
+
+// a single-CTA solve is bound by exposed instruction latency (two warps per scheduler at 256 threads): it runs 512
+// threads; the multi-CTA grid keeps 256-thread CTAs
+static int lg_threads(int G) {
+#ifdef TTIPM_EMU
+    (void)G;
+    return block_threads();
+#else
+    return G == 1 ? g_single_cta_threads : 256;
+#endif
 }
 
 struct LgInfoParams {
@@ -537,12 +621,12 @@ extern "C" int ttipm_local_lgmres(int ineq, const ttipm_term* K00, const ttipm_t
             optin_done = 1;
         }
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lgmres, block_threads(), smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lgmres, lg_threads(G), smem);
         if (per_sm < 1) return fail(4, "lgmres: kernel does not fit on an SM with %d B shared memory", smem);
         if (G > per_sm * di.sms) return fail(4, "lgmres: grid %d not co-resident", G);
     }
 #endif
-    rc = launch_kernel("k_lgmres", k_lgmres, dim3(G), dim3(block_threads()), smem, st, true, p);
+    rc = launch_kernel("k_lgmres", k_lgmres, dim3(G), dim3(lg_threads(G)), smem, st, true, p);
     if (rc) return rc;
     if (info) {
         // info[0..3] = its, matvecs, reason, cycles (as doubles), info[4] = final residual estimate, info[5] = grid

@@ -72,6 +72,58 @@ static inline int mv_plan(MvGeom& g, int l, int L, int r, int R, int nm, int sma
 }
 
 #if defined(__CUDACC__) || defined(TTIPM_EMU)
+// Small local blocks (the small / medium regime: r, R <= ~8, operator ranks <= ~6): each stage has only a few hundred
+// outputs with inner dimensions of 4..24, where the DMMA tile machinery of tgemm (offset tables, three block barriers
+// and a dependent tensor-core chain per stage) costs ~1.3 us per stage against ~0.1 us of arithmetic.  Here every
+// thread computes whole output elements with plain FMAs straight from the strided operands; one barrier per stage.
+// Same contraction order as the reference's 3-GEMM chain (cy_src/lgmres_cy.pyx:146-153).
+TT_DEV bool mv_term_is_small(const MvTerm& t, const MvGeom& g, int Ltc) {
+    const int n1 = g.r * Ltc * g.nm * t.S, n2 = t.s * g.r * g.nm * Ltc, n3 = g.l * g.nm * Ltc;
+    const int lim = 4 * (int)blockDim.x;
+    return n1 <= lim && n2 <= lim && n3 <= lim && g.R <= 32 && g.nm * t.S <= 64 && t.s * g.r <= 64;
+}
+TT_DEV void mv_accumulate_term_small(const MvTerm& t, const double* __restrict__ x_blk, int x_rs, int x_ns, const MvGeom& g,
+                                     int L0, int Ltc, double* smem) {
+    double* T1 = smem + g.oT1;
+    double* T2 = smem + g.oT2;
+    double* Ys = smem + g.oYs;
+    const int r = g.r, R = g.R, nm = g.nm, l = g.l, s = t.s, S = t.S;
+    const int ld1 = g.ld1, ld2 = g.ld2, ldY = g.ldY;
+    __syncthreads();                         // T1 / T2 of the previous term are no longer read
+    // stage 1: T1[(rho, lt), (nu, sig')] = sum_P x[rho, nu, P] P2[L0 + lt, sig', P]
+    for (int i = threadIdx.x; i < r * Ltc * nm * S; i += blockDim.x) {
+        const int sp = i % S, nu = (i / S) % nm, lt = (i / (S * nm)) % Ltc, rho = i / (S * nm * Ltc);
+        const double* xp = x_blk + (long)rho * x_rs + (long)nu * x_ns;
+        const double* pp = t.P2 + (long)(L0 + lt) * t.p2s[0] + (long)sp * t.p2s[1];
+        double acc = 0.0;
+        for (int P = 0; P < R; ++P) acc += xp[P] * pp[(long)P * t.p2s[2]];
+        T1[(rho * Ltc + lt) * ld1 + nu * S + sp] = acc;
+    }
+    __syncthreads();
+    // stage 2: T2[(sig, rho), (mu, lt)] = sum_(nu, sig') T1[(rho, lt), (nu, sig')] A[sig, mu, nu, sig']
+    for (int i = threadIdx.x; i < s * r * nm * Ltc; i += blockDim.x) {
+        const int lt = i % Ltc, mu = (i / Ltc) % nm, rho = (i / (Ltc * nm)) % r, sg = i / (Ltc * nm * r);
+        const double* tp = T1 + (rho * Ltc + lt) * ld1;
+        const double* ap = t.A + (long)sg * t.as_[0] + (long)mu * t.as_[1];
+        double acc = 0.0;
+        for (int nu = 0; nu < nm; ++nu)
+            for (int sp = 0; sp < S; ++sp) acc += tp[nu * S + sp] * ap[(long)nu * t.as_[2] + (long)sp * t.as_[3]];
+        T2[(sg * r + rho) * ld2 + mu * Ltc + lt] = acc;
+    }
+    __syncthreads();
+    // stage 3: Ys[lam, (mu, lt)] += alpha sum_(sig, rho) P1[lam, sig, rho] T2[(sig, rho), (mu, lt)]
+    const double alpha = t.alpha;
+    for (int i = threadIdx.x; i < l * nm * Ltc; i += blockDim.x) {
+        const int c = i % (nm * Ltc), lam = i / (nm * Ltc);
+        const double* pp = t.P1 + (long)lam * t.p1s[0];
+        double acc = 0.0;
+        for (int sg = 0; sg < s; ++sg)
+            for (int rho = 0; rho < r; ++rho) acc += pp[(long)sg * t.p1s[1] + (long)rho * t.p1s[2]] * T2[(sg * r + rho) * ld2 + c];
+        Ys[lam * ldY + c] += alpha * acc;
+    }
+    __syncthreads();
+}
+
 // Accumulate alpha * (term applied to x_blk) for L-tile [L0, L0+Ltc) into Ys (l x ldY, column (m, Lt)).
 //   x_blk: element (rho, nu, Rho) at x_blk[rho * x_rs + nu * x_ns + Rho]
 TT_DEV void mv_accumulate_term(const MvTerm& t, const double* __restrict__ x_blk, int x_rs, int x_ns, const MvGeom& g,
@@ -83,6 +135,10 @@ TT_DEV void mv_accumulate_term(const MvTerm& t, const double* __restrict__ x_blk
     int* offs = (int*)(smem + g.oOffs);
     const int r = g.r, R = g.R, nm = g.nm, l = g.l, s = t.s, S = t.S;
     const int ld1 = g.ld1, ld2 = g.ld2, ldA = g.ldA, ldY = g.ldY;
+    if (mv_term_is_small(t, g, Ltc)) {
+        mv_accumulate_term_small(t, x_blk, x_rs, x_ns, g, L0, Ltc, smem);
+        return;
+    }
 
     // operator core -> As[(nu, sig'), (sig, mu)]
     for (int i = threadIdx.x; i < nm * S * s * nm; i += blockDim.x) {
