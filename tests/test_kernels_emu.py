@@ -125,3 +125,33 @@ def test_elementwise(rt):
 
 def test_tt_algebra(rt):
     KC.assert_small(KC.case_tt_algebra(rt))
+
+
+def test_tt_products_above_als_threshold(rt):
+    """rank products above the reference's ALS thresholds (80 mat-vec / 40 mat-mat, src/tt_als.py:1632,1766): the
+    dispatchers form the exact zip-up product and round to op_tol -- dense results agree with NumPy to that tolerance"""
+    import numpy as np
+    from ttipm_b200 import tt as T, use_runtime
+    rng = np.random.default_rng(3)
+
+    def dense(tt):
+        d = tt[0]
+        for c in tt[1:]:
+            d = np.tensordot(d, c, axes=(-1, 0))
+        return d.squeeze(0).squeeze(-1)
+
+    rm, rv = 9, 10                                                # 90 > 80
+    mat = [rng.standard_normal((1, 4, 4, rm)), rng.standard_normal((rm, 4, 4, 1))]
+    vec = [rng.standard_normal((1, 4, rv)), rng.standard_normal((rv, 4, 1))]
+    with use_runtime(rt):
+        out = T.tt_mat_vec_mul(mat, vec, 1e-10, 1e-12)
+    want = np.einsum("imjn,mn->ij", dense(mat), dense(vec))      # cores (1, i, m, r), (r, j, n, 1)
+    got = dense(out)
+    assert np.linalg.norm(got - want) <= 1e-8 * np.linalg.norm(want)
+    m2 = [rng.standard_normal((1, 4, 4, 7)), rng.standard_normal((7, 4, 4, 1))]      # 9 * 7 = 63 > 40
+    with use_runtime(rt):
+        out2 = T.tt_mat_mat_mul(mat, m2, 1e-10, 1e-12)
+    A = dense(mat)          # (i, m, j, n): cores (1, i, m, r), (r, j, n, 1)
+    B = dense(m2)
+    want2 = np.einsum("imjn,mpnq->ipjq", A, B)
+    assert np.linalg.norm(dense(out2) - want2) <= 1e-8 * np.linalg.norm(want2)
