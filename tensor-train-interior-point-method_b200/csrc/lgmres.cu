@@ -49,6 +49,8 @@ struct LgParams {
     // of matvec.cuh a matvec then never waits for L2 (each of its ~15 dependent stages otherwise pays 1-4 L2 round trips)
     int stage;                // 1: stage operands (grid of one CTA and enough shared memory)
     int oStage;               // offset of the staging area (doubles): [term copies][operand data][vector nv]
+    int oTiny;                // single-CTA matvec scratch: per term T1 (r R n S) and T2 (s r n R), then tmp (m)
+    int tinyT1[12], tinyT2[12], tinyTmp;   // offsets inside that scratch, terms in the order tA[0..nA), tB[0..nB)
     int oHess;                // CTA 0: Givens cosines / sines, rotated rhs, working Hessenberg column, back-substitution
                               // vector in shared memory (5 x (max_k + 2) doubles, outside the matvec / CGS scratch)
 };
@@ -94,6 +96,8 @@ TT_DEV void lg_item(LgCtx& c, const MvTerm* terms, int nterms, int slot, int til
     __syncthreads();
 }
 
+TT_DEV void lg_apply_tiny(LgCtx& c, const double* src, double* dst);
+
 // dst = Op(src); src must be globally visible on entry, dst is globally visible on exit
 TT_DEV void lg_apply(LgCtx& c, const double* src, double* dst) {
     const LgParams& p = c.p;
@@ -102,13 +106,85 @@ TT_DEV void lg_apply(LgCtx& c, const double* src, double* dst) {
         __syncthreads();
         for (int e = threadIdx.x; e < p.nv; e += blockDim.x) c.xs[e] = src[e];
         __syncthreads();
-        src = c.xs;
+        lg_apply_tiny(c, c.xs, dst);
+        return;
     }
     for (int it = blockIdx.x; it < p.nslotA * nt; it += gridDim.x)
         lg_item(c, c.tA, p.nA, p.slotA[it / nt], it % nt, src, dst);
     c.sync();
     for (int it = blockIdx.x; it < nt; it += gridDim.x) lg_item(c, c.tB, p.nB, 1, it, src, dst);
     c.sync();
+}
+
+// Single-CTA matvec on staged operands: ncu showed the one-term-at-a-time form waiting at block barriers 58 % of the
+// time (~30 barriers per matvec, each phase a short dependent chain on a few hundred outputs).  Here all terms of a
+// phase advance together: stage 1 of every term, barrier, stage 2 of every term, barrier, stage 3 per output slot,
+// barrier -- 6 barriers per matvec, each phase with 1000+ independent outputs for the 512 threads.
+// Arithmetic per output = the same 3-GEMM chain as mv_accumulate_term_small (reference cy_src/lgmres_cy.pyx:146-153).
+TT_DEV void lg_apply_tiny(LgCtx& c, const double* src, double* dst) {
+    const LgParams& p = c.p;
+    const int r = p.g.r, R = p.g.R, nm = p.g.nm, m = p.m, nth = blockDim.x, tid = threadIdx.x;
+    double* tb = c.smem + p.oTiny;
+    double* tmpS = tb + p.tinyTmp;
+    for (int phase = 0; phase < 2; ++phase) {
+        const MvTerm* T = phase ? c.tB : c.tA;
+        const int nT = phase ? p.nB : p.nA, q0 = phase ? p.nA : 0;
+        // ---- stage 1: T1[(rho, Lam), (nu, sig')] = sum_P x[rho, nu, P] P2[Lam, sig', P] ----
+        int tot = 0;
+        for (int q = 0; q < nT; ++q) tot += r * R * nm * T[q].S;
+        for (int i = tid; i < tot; i += nth) {
+            int q = 0, j = i;
+            while (j >= r * R * nm * T[q].S) { j -= r * R * nm * T[q].S; ++q; }
+            const int S = T[q].S;
+            const int sp = j % S, nu = (j / S) % nm, Lam = (j / (S * nm)) % R, rho = j / (S * nm * R);
+            const double* xin = T[q].in_blk == 3 ? tmpS : src + T[q].in_blk * m;
+            const double* xp = xin + (rho * nm + nu) * R;
+            const double* pp = T[q].P2 + (Lam * S + sp) * R;
+            double acc = 0.0;
+            for (int P = 0; P < R; ++P) acc += xp[P] * pp[P];
+            tb[p.tinyT1[q0 + q] + j] = acc;               // j = ((rho * R + Lam) * nm + nu) * S + sp
+        }
+        __syncthreads();
+        // ---- stage 2: T2[(sig, rho), (mu, Lam)] = sum_(nu, sig') T1[(rho, Lam), (nu, sig')] A[sig, mu, nu, sig'] ----
+        tot = 0;
+        for (int q = 0; q < nT; ++q) tot += T[q].s * r * nm * R;
+        for (int i = tid; i < tot; i += nth) {
+            int q = 0, j = i;
+            while (j >= T[q].s * r * nm * R) { j -= T[q].s * r * nm * R; ++q; }
+            const int S = T[q].S;
+            const int Lam = j % R, mu = (j / R) % nm, rho = (j / (R * nm)) % r, sg = j / (R * nm * r);
+            const double* tp = tb + p.tinyT1[q0 + q] + (rho * R + Lam) * nm * S;
+            const double* ap = T[q].A + (sg * nm + mu) * nm * S;
+            double acc = 0.0;
+            for (int k = 0; k < nm * S; ++k) acc += tp[k] * ap[k];
+            tb[p.tinyT2[q0 + q] + j] = acc;               // j = ((sig * r + rho) * nm + mu) * R + Lam
+        }
+        __syncthreads();
+        // ---- stage 3 per output slot: y[lam, mu, Lam] = sum_terms alpha sum_(sig, rho) P1[lam, sig, rho] T2[...] ----
+        const int nslot = phase ? 1 : p.nslotA;
+        for (int i = tid; i < nslot * m; i += nth) {
+            const int slot = phase ? 1 : p.slotA[i / m], o = i % m;
+            const int c_ = o % (nm * R), lam = o / (nm * R);
+            double v = 0.0;
+            for (int q = 0; q < nT; ++q) {
+                if (T[q].out_blk != slot) continue;
+                const int sr = T[q].s * r;
+                const double* pp = T[q].P1 + lam * sr;
+                const double* t2 = tb + p.tinyT2[q0 + q] + c_;
+                double acc = 0.0;
+                for (int k = 0; k < sr; ++k) acc += pp[k] * t2[k * nm * R];
+                v += T[q].alpha * acc;
+            }
+            if (slot == 3) {
+                v *= p.inv_I[o];
+                if (p.nblk == 3) v += src[2 * m + o];
+                tmpS[o] = v;
+            } else {
+                dst[(long)slot * m + o] = v;
+            }
+        }
+        __syncthreads();
+    }
 }
 
 // copy the logical (d0, d1, d2[, d3]) tensor addressed by `strides` to a contiguous block of shared memory
@@ -519,10 +595,18 @@ static int lg_setup(LgParams& p, int ineq, const ttipm_term* K00, const ttipm_te
             for (int i = 0; i < p.nA; ++i) data += (long)r * p.tA[i].s * r + (long)p.tA[i].s * nmode * nmode * p.tA[i].S + (long)R * p.tA[i].S * R;
             for (int i = 0; i < p.nB; ++i) data += (long)r * p.tB[i].s * r + (long)p.tB[i].s * nmode * nmode * p.tB[i].S + (long)R * p.tB[i].S * R;
             const long o = (bytes + 15) / 16 * 2;
-            if ((o + data) * 8 <= di.smem_optin) {
+            long tiny = 0;
+            for (int i = 0; i < p.nA + p.nB; ++i) {
+                const MvTerm& t = i < p.nA ? p.tA[i] : p.tB[i - p.nA];
+                p.tinyT1[i] = (int)tiny; tiny += (long)r * R * nmode * t.S;
+                p.tinyT2[i] = (int)tiny; tiny += (long)t.s * r * nmode * R;
+            }
+            p.tinyTmp = (int)tiny; tiny += p.m;
+            if ((o + data + tiny) * 8 <= di.smem_optin) {
                 p.stage = 1;
                 p.oStage = (int)o;
-                bytes = (int)((o + data) * 8);
+                p.oTiny = (int)(o + data);
+                bytes = (int)((o + data + tiny) * 8);
             }
         }
         if (bytes <= di.smem_optin) {
