@@ -52,7 +52,7 @@ struct LgParams {
     int oTiny;                // single-CTA matvec scratch: per term T1 (r R n S) and T2 (s r n R), then tmp (m)
     int tinyT1[12], tinyT2[12], tinyTmp;   // offsets inside that scratch, terms in the order tA[0..nA), tB[0..nB)
     int oHess;                // CTA 0: Givens cosines / sines, rotated rhs, working Hessenberg column, back-substitution
-                              // vector in shared memory (5 x (max_k + 2) doubles, outside the matvec / CGS scratch)
+                              // vector (5 x (max_k + 2) doubles) and three control words in shared memory, outside the matvec / CGS scratch
 };
 
 #define LG_STAGE_TERM_DOUBLES ((int)((12 * sizeof(MvTerm) + 7) / 8))
@@ -64,7 +64,9 @@ struct LgCtx {
     const MvTerm* tA;         // phase A / B term lists: the kernel parameters, or their shared-memory staged copies
     const MvTerm* tB;
     double* xs;               // staged input vector (nullptr when not staging)
-    TT_DEVM LgCtx(const LgParams& pp, double* s) : p(pp), smem(s), epoch(0), tA(pp.tA), tB(pp.tB), xs(nullptr) {}
+    double* wcopy;            // single-CTA mode: the matvec also leaves its result here (the CGS work vector)
+    TT_DEVM LgCtx(const LgParams& pp, double* s)
+        : p(pp), smem(s), epoch(0), tA(pp.tA), tB(pp.tB), xs(nullptr), wcopy(nullptr) {}
     TT_DEVM void sync() { grid_sync(p.barrier, epoch); }
 };
 
@@ -181,6 +183,7 @@ TT_DEV void lg_apply_tiny(LgCtx& c, const double* src, double* dst) {
                 tmpS[o] = v;
             } else {
                 dst[(long)slot * m + o] = v;
+                if (c.wcopy) c.wcopy[slot * m + o] = v;
             }
         }
         __syncthreads();
@@ -265,9 +268,12 @@ TT_GLOBAL void __launch_bounds__(512) k_lgmres(const LgParams p) {
     double* grs = ss + (p.max_k + 2);
     double* colS = grs + (p.max_k + 2);
     double* tS = colS + (p.max_k + 2);
+    double* ctlS = tS + (p.max_k + 2);      // single-CTA mode: residual estimate, rotated rhs entry, null-pivot flag
     const bool lead = blockIdx.x == 0 && tid == 0;
     const bool lead_warp = blockIdx.x == 0 && wid == 0;
     if (p.stage) lg_stage_operands(c);
+    const bool tiny = p.stage != 0;            // single CTA, operands staged
+    if (tiny) c.wcopy = wS;
 
     if (p.mode == LG_APPLY) {
         lg_apply(c, p.b, p.x);
@@ -339,20 +345,32 @@ TT_GLOBAL void __launch_bounds__(512) k_lgmres(const LgParams p) {
                 const double* src = p.AAUG + (long)spot * nv;
                 for (int e = e0 + tid; e < e1; e += nth) Vn[e] = src[e];
             }
-            // classical Gram-Schmidt, one pass: partial dots over the CTA's chunk
-            __syncthreads();
-            for (int e = e0 + tid; e < e1; e += nth) wS[e - e0] = Vn[e];
-            __syncthreads();
+            // classical Gram-Schmidt, one pass: partial dots over the CTA's chunk.  A single-CTA solve (tiny) keeps every
+            // partial result in shared memory: no global partial sums, no L2 round trips, half the barriers
+            const bool from_matvec = tiny && loc_it < it_arnoldi;
+            if (!from_matvec) {
+                __syncthreads();
+                for (int e = e0 + tid; e < e1; e += nth) wS[e - e0] = Vn[e];
+                __syncthreads();
+            }
             for (int i = wid; i <= loc_it; i += nw) {
                 const double* Vi = p.V + (long)i * nv;
                 double d = 0.0;
                 for (int e = e0 + lane; e < e1; e += 32) d += Vi[e] * wS[e - e0];
                 d = warp_sum(d);
-                if (lane == 0) mypart[i] = d;
+                if (lane == 0) {
+                    if (tiny) hS[i] = d;
+                    else mypart[i] = d;
+                }
             }
-            c.sync();
-            for (int i = tid; i <= loc_it; i += nth) hS[i] = lg_sum_partials(p, i);
-            __syncthreads();
+            if (tiny) {
+                __syncthreads();
+            } else {
+                c.sync();
+                for (int i = tid; i <= loc_it; i += nth) hS[i] = lg_sum_partials(p, i);
+                __syncthreads();
+            }
+            double tt;
             {
                 double s2 = 0.0;
                 for (int e = e0 + tid; e < e1; e += nth) {
@@ -362,10 +380,14 @@ TT_GLOBAL void __launch_bounds__(512) k_lgmres(const LgParams p) {
                     s2 += w * w;
                 }
                 s2 = block_sum(s2, scr);
-                if (tid == 0) mypart[p.max_k + 2] = s2;
+                if (tiny) {
+                    tt = sqrt(s2);
+                } else {
+                    if (tid == 0) mypart[p.max_k + 2] = s2;
+                    c.sync();
+                    tt = sqrt(lg_sum_partials(p, p.max_k + 2));
+                }
             }
-            c.sync();
-            const double tt = sqrt(lg_sum_partials(p, p.max_k + 2));
             double hapbnd = fabs(tt / grs_loc);
             if (hapbnd > p.haptol) hapbnd = p.haptol;
             if (tt > hapbnd) {
@@ -391,10 +413,12 @@ TT_GLOBAL void __launch_bounds__(512) k_lgmres(const LgParams p) {
                         colS[j + 1] = cc[j] * colS[j + 1] - ss[j] * t0;
                     }
                     double newres = 0.0;
+                    ctlS[2] = 0.0;
                     if (!hapend) {
                         const double t0 = sqrt(colS[loc_it] * colS[loc_it] + colS[loc_it + 1] * colS[loc_it + 1]);
                         if (t0 == 0.0) {
                             p.ctrl_i[0] = 1;
+                            ctlS[2] = 1.0;
                         } else {
                             cc[loc_it] = colS[loc_it] / t0;
                             ss[loc_it] = colS[loc_it + 1] / t0;
@@ -406,17 +430,19 @@ TT_GLOBAL void __launch_bounds__(512) k_lgmres(const LgParams p) {
                     }
                     p.ctrl_d[0] = newres;
                     p.ctrl_d[1] = grs[loc_it + 1];
+                    ctlS[0] = newres;               // single-CTA mode reads these back from shared memory
+                    ctlS[1] = grs[loc_it + 1];
                 }
                 __syncwarp();
                 for (int i = lane; i <= loc_it + 1; i += 32) col[i] = colS[i];
             }
             c.sync();
-            if (ld_cg_i(&p.ctrl_i[0]) != 0) {
+            if (tiny ? ctlS[2] != 0.0 : ld_cg_i(&p.ctrl_i[0]) != 0) {
                 reason = R_NULL;
                 break;
             }
-            res = ld_cg(&p.ctrl_d[0]);
-            grs_loc = ld_cg(&p.ctrl_d[1]);
+            res = tiny ? ctlS[0] : ld_cg(&p.ctrl_d[0]);
+            grs_loc = tiny ? ctlS[1] : ld_cg(&p.ctrl_d[1]);
             ++loc_it;
             ++its;
             reason = lg_converged(p, its, res, ttol, rnorm0);
@@ -587,7 +613,7 @@ static int lg_setup(LgParams& p, int ineq, const ttipm_term* K00, const ttipm_te
         const int cgs_bytes = (p.oScr + 40) * 8;
         int bytes = imax(p.g.smem_bytes, cgs_bytes);
         p.oHess = (bytes + 15) / 16 * 2;
-        bytes = (p.oHess + 5 * (max_k + 2)) * 8;
+        bytes = (p.oHess + 5 * (max_k + 2) + 4) * 8;
         p.stage = 0;
         p.oStage = 0;
         if (G == 1) {
