@@ -334,8 +334,12 @@ def main():
 
     clocks = Clocks(local_rank)
     clocks.start()                 # sampler runs through the warm-up too (its first NVML queries are slow) ...
+    warm_times = []
     for _ in range(args.warmup):
-        device_pass()
+        # same object lifetimes as in the timed loop: the previous pass's solver objects (device buffers, pinned staging)
+        # stay alive until the next pass has returned
+        t, nl, solvers, outs = device_pass()
+        warm_times.append(t)
     barrier()
     clocks.samples.clear()         # ... but only samples of the timed region are reported
     clocks.reasons.clear()
@@ -436,6 +440,7 @@ def main():
             "kernels": kernels,
             "krylov": {"solves": lg_calls, "inner_iterations": lg_its},
             "step_seconds": [float(t) for t in times],
+            "warmup_step_seconds": [float(t) for t in warm_times],
             "final_local_residuals": res_check,
         }
         if not args.no_cpu_baseline:

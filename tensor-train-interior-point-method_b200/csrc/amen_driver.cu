@@ -69,16 +69,26 @@ void dev_free(Ctx& c, void* p, size_t bytes) {
 #endif
     c.bytes_live -= bytes;
 }
+// The pinned staging buffer for scalar read-backs is process wide (like the library handles below): cudaMallocHost /
+// cudaFreeHost cost hundreds of microseconds and serialise the device, and a drop-in run creates one solver object per
+// Newton system.  One caller thread and one stream per process, so the buffer is never shared concurrently.
+static double* g_pinned = nullptr;
+static size_t g_pinned_cap = 0;
 static void ensure_pinned(Ctx& c, size_t n) {
-    if (c.pinned_cap >= n) return;
+    if (g_pinned_cap < n) {
+        const size_t want = n < 4096 ? 4096 : n + n / 2;
 #ifdef TTIPM_EMU
-    free(c.pinned);
-    c.pinned = (double*)malloc(n * sizeof(double));
+        free(g_pinned);
+        g_pinned = (double*)malloc(want * sizeof(double));
 #else
-    if (c.pinned) cudaFreeHost(c.pinned);
-    if (cudaMallocHost((void**)&c.pinned, n * sizeof(double)) != cudaSuccess) throw DriverError(91, "pinned allocation failed");
+        if (g_pinned) cudaFreeHost(g_pinned);
+        g_pinned = nullptr;
+        if (cudaMallocHost((void**)&g_pinned, want * sizeof(double)) != cudaSuccess) throw DriverError(91, "pinned allocation failed");
 #endif
-    c.pinned_cap = n;
+        g_pinned_cap = want;
+    }
+    c.pinned = g_pinned;
+    c.pinned_cap = g_pinned_cap;
 }
 void to_host(Ctx& c, const double* dev, size_t n, double* host) {
 #ifdef TTIPM_EMU
@@ -1156,12 +1166,7 @@ extern "C" ttipm_amen* ttipm_amen_create(int d, int block_size, int ineq, void* 
 
 extern "C" void ttipm_amen_destroy(ttipm_amen* h) {
     if (!h) return;
-#ifndef TTIPM_EMU
-    if (h->a.c.pinned) cudaFreeHost(h->a.c.pinned);
-#else
-    free(h->a.c.pinned);
-#endif
-    h->a.c.pinned = nullptr;
+    h->a.c.pinned = nullptr;          // the staging buffer is process wide (ensure_pinned)
     delete h;
 }
 
