@@ -142,6 +142,9 @@ int ttipm_local_lgmres(int ineq, const ttipm_term* K00, const ttipm_term* K01, c
  * matrices use one CTA per matrix.  The setter returns the previous threshold (default 17); min_dim <= 0 only queries. */
 int ttipm_linalg_coop_min_dim(int min_dim);
 
+/* Threads per CTA of the QR / SVD kernel (256 or 512; tuning hook).  Returns the previous value; any other argument
+ * only queries. */
+int ttipm_linalg_threads(int threads);
 /* Tall SVDs (M >= N) are preconditioned by three QR factorisations (A = Q1 R1, R1^T = Q2 R2, R2^T = Q3 R3; Jacobi on the
  * rows of R3 with a K x K accumulator): 1 (default) / 0 = single QR with the K x M accumulator.  Returns the previous
  * setting; a negative argument only queries. */

@@ -629,6 +629,7 @@ static int g_coop_min_dim = 17;
 static int g_resident_max_dim = 32;
 static double g_floor_factor = 0.0;
 static int g_tall_triple_qr = 1;
+static int g_coop_threads = 256;
 
 struct LinPlan {
     LinParams p;
@@ -666,7 +667,7 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
 #ifdef TTIPM_EMU
     pl.threads = block_threads();
 #else
-    pl.threads = 256;
+    pl.threads = g_coop_threads;
 #endif
     const int nw = pl.threads / 32;
     p.ldp = p.M1 + (p.M1 & 1);
@@ -748,6 +749,12 @@ using namespace ttipm;
 extern "C" int ttipm_linalg_coop_min_dim(int min_dim) {
     const int old = g_coop_min_dim;
     if (min_dim > 0) g_coop_min_dim = min_dim;
+    return old;
+}
+
+extern "C" int ttipm_linalg_threads(int threads) {
+    const int old = g_coop_threads;
+    if (threads == 256 || threads == 512) g_coop_threads = threads;
     return old;
 }
 
