@@ -598,13 +598,11 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
     if (p.triple) {
         lin_apply_q(c, W1, tau1, M1, K, K, 1, Jt, ord, U, 1, K);               // U columns = Q1 [(Q3 J) column; 0]
         lin_apply_q(c, W2, tau2, K, K, K, 1, G, ord, Wt, N, 1);                // W rows = Q2 g  (N == K)
-    } else {
-        for (long i = gtid; i < (long)M * K; i += gth) U[i] = ld_cg(Jt + (long)ord[i % K] * Mj + i / K);
-    }
-    if (p.triple) {
     } else if (!wide) {
+        for (long i = gtid; i < (long)M * K; i += gth) U[i] = ld_cg(Jt + (long)ord[i % K] * Mj + i / K);
         for (long i = gtid; i < (long)K * N; i += gth) Wt[i] = ld_cg(G + (long)ord[i / N] * K + i % N);
     } else {
+        for (long i = gtid; i < (long)M * K; i += gth) U[i] = ld_cg(Jt + (long)ord[i % K] * Mj + i / K);
         lin_apply_q(c, W1, tau1, M1, K, K, 1, G, ord, Wt, N, 1);               // W rows = Q1 [g; 0]
     }
     if (gtid == 0 && p.info) {
