@@ -6,6 +6,7 @@ does not.
   python oracle/ref_harness/make_golden.py kernels
   python oracle/ref_harness/make_golden.py amen maxcut 5 1 319 0,1,5 [--budget 600]
   python oracle/ref_harness/make_golden.py e2e maxcut 5 1 319
+  python oracle/ref_harness/make_golden.py als
 
 File formats (all float64 unless noted):
   kernels_*.npz : flat dict "case/<name>/in_*", ".../out_*"
@@ -190,6 +191,35 @@ def kernels():
     print("wrote kernels.npz with", len(out), "arrays")
 
 
+def als():
+    """ALS-fitted TT products (reference src/tt_als.py:1502-1762): inputs, the NumPy seed set
+    before the call, the reference's result cores.  als_products.npz: "<case>/A|D|out/<k>", "<case>/seed|tol"."""
+    ref = ref_env.load()
+    ALS = ref.tt_als
+    rng = np.random.default_rng(20251019)
+    out = {}
+    cases = {
+        "matvec_d5": ("vec", [3, 5, 5, 3], [4, 6, 6, 4], 2, 1e-6),
+        "matvec_d6": ("vec", [2, 4, 6, 4, 2], [3, 8, 9, 8, 3], 4, 1e-4),
+        "matmat_d4": ("mat", [3, 4, 3], [2, 5, 2], 2, 1e-6),
+        "matmat_d5": ("mat", [2, 3, 3, 2], [3, 4, 4, 3], 4, 1e-4),
+    }
+    for seed, (name, (kind, ra, rd, n, tol)) in enumerate(cases.items(), start=101):
+        A = _rand_tt(rng, ra, (n, n))
+        D = _rand_tt(rng, rd, (n,) if kind == "vec" else (n, n))
+        fn = ALS.tt_approx_mat_vec_mul if kind == "vec" else ALS.tt_approx_mat_mat_mul
+        np.random.seed(seed)
+        res = fn(_cp(A), _cp(D), tol=tol)
+        _put_tt(out, name + "/A", A)
+        _put_tt(out, name + "/D", D)
+        _put_tt(out, name + "/out", res)
+        out[name + "/seed"] = np.array(seed)
+        out[name + "/tol"] = np.array(tol)
+        print(name, "ranks", [c.shape[-1] for c in res[:-1]])
+    np.savez_compressed(os.path.join(GOLD, "als_products.npz"), **out)
+    print("wrote als_products.npz with", len(out), "arrays")
+
+
 class _Budget(BaseException):
     pass
 
@@ -337,5 +367,7 @@ if __name__ == "__main__":
         amen(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]),
              set(int(v) for v in sys.argv[6].split(",")), budget, local="--local" in sys.argv,
              inputs_only="--inputs-only" in sys.argv)
+    elif cmd == "als":
+        als()
     elif cmd == "e2e":
         e2e(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))

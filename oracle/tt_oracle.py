@@ -559,18 +559,150 @@ def tt_fast_hadamard(a, b, eps=1e-18):
     return _zipup(first3, len(a), cores, eps)
 
 
+def symmetric_powers_of_two(length):
+    """cy_src/tt_ops_cy.pyx:538-555: 2, 4, 8, ... rising to the middle bond and mirrored."""
+    half = (length + 1) // 2
+    up = [1 << (i + 1) for i in range(half)]
+    return np.array((up + up[:length // 2][::-1])[:length] if length > 0 else [], dtype=np.int64)
+
+
+def add_kick_rank(u, v, r_add=2):
+    """cy_src/tt_ops_cy.pyx:559-579: enrich the orthonormal factor with r_add Gaussian columns
+    (global RNG), re-orthogonalise, carry the R factor into v."""
+    old_r = u.shape[1]
+    uk = np.random.randn(u.shape[0], r_add)
+    q, rm = sla.qr(np.ascontiguousarray(np.concatenate((u, uk), axis=1)), mode="economic", check_finite=False)
+    return q, rm[:, :old_r] @ v, q.shape[1]
+
+
+def _als_fit_product(A, D, x0, kick_rank, nswp, tol, trace=None):
+    """ALS fit of the TT product A*D, one engine for
+    tt_approx_mat_mat_mul (src/tt_als.py:1502-1628, D cores (b,k,n,B)) and
+    tt_approx_mat_vec_mul (src/tt_als.py:1637-1762, D cores (b,k,B) handled as n = 1).
+
+    State as in the reference: unit-norm interfaces G[k] (r, a, b) with their norms in
+    normAD, unit-norm non-orthogonal neighbour cores with their norms in normx, and the
+    running scale nrmsc that converts a raw local contraction into the local solution."""
+    vec = D[0].ndim == 3
+    D4 = [c.reshape(c.shape[0], c.shape[1], 1, c.shape[2]) for c in D] if vec else D
+    if x0 is None:
+        max_ranks = np.maximum((np.array(tt_ranks(A)) + np.array(tt_ranks(D))) / 2, 2).astype(int)
+        x = tt_random_gaussian(list(max_ranks), (A[0].shape[2],) if vec else A[0].shape[1:-1])
+    else:
+        x, max_ranks = x0, np.array(tt_ranks(x0))
+    if kick_rank is None:
+        kick_rank = np.maximum((symmetric_powers_of_two(len(A) - 1) - max_ranks) / (nswp / 2), 2).astype(int)
+    d = len(x)
+    x = [c.reshape(c.shape[0], c.shape[1], 1, c.shape[2]) if vec else c for c in x]
+    rx = np.array([1] + tt_ranks(x) + [1])
+    G = [np.ones((1, 1, 1))] + [None] * (d - 1) + [np.ones((1, 1, 1))]
+    normAD, normx, nrmsc = np.ones(d - 1), np.ones(d - 1), 1.0
+    tol = tol / np.sqrt(d)
+    st = {"max_res": 0.0}
+
+    def local(k):
+        sol = np.einsum("rab,amkA,bknB,RAB->rmnR", G[k], A[k], D4[k], G[k + 1], optimize="greedy") * nrmsc
+        res = np.linalg.norm(sol - x[k]) / max(np.linalg.norm(sol), 1e-8)
+        st["max_res"] = max(st["max_res"], res)
+        return sol
+
+    def split(mat, bond, last):
+        u, s, v = sla.svd(mat, full_matrices=False, check_finite=False, lapack_driver="gesvd")
+        v = s.reshape(-1, 1) * v
+        r = prune_singular_vals(s, tol)
+        if not last:
+            return add_kick_rank(u[:, :r], v[:r], kick_rank[bond])
+        return u[:, :r], v[:r], r
+
+    last = False
+    for swp in range(nswp):
+        st["max_res"] = np.inf if swp == 0 else 0.0
+        for k in range(d - 1, -1, -1):                                   # :1531-1565 / :1666-1700
+            sol = local(k) if swp > 0 else x[k]
+            nm = x[k].shape[1:3]
+            if k == 0:
+                x[k] = sol.reshape(rx[k], *nm, rx[k + 1])
+                continue
+            u, v, r = split(sol.reshape(rx[k], -1).T, k - 1, last)
+            nrmsc *= normx[k - 1] / normAD[k - 1]
+            x[k] = u.T.reshape(r, *nm, rx[k + 1])
+            x[k - 1] = np.tensordot(x[k - 1], v.T, axes=([3], [0]))
+            nrm = np.linalg.norm(x[k - 1])
+            normx[k - 1] *= nrm
+            x[k - 1] = x[k - 1] / nrm
+            rx[k] = r
+            G[k] = np.einsum("RAB,amkA,bknB,rmnR->rab", G[k + 1], A[k], D4[k], x[k], optimize="greedy")
+            nrm = np.linalg.norm(G[k])
+            nrm = nrm if nrm > 0 else 1.0
+            G[k] = G[k] / nrm
+            normAD[k - 1] = nrm
+            nrmsc *= normAD[k - 1] / normx[k - 1]
+        if trace is not None:
+            trace.append(("bck", swp, float(st["max_res"]), [int(q) for q in rx]))
+        if last:
+            break
+        if st["max_res"] < tol or swp == nswp - 1:
+            last = True
+        st["max_res"] = 0.0
+        for k in range(d):                                               # :1571-1605 / :1706-1740
+            sol = local(k)
+            nm = x[k].shape[1:3]
+            if k == d - 1:
+                x[k] = sol.reshape(rx[k], *nm, rx[k + 1])
+                continue
+            nrmsc *= normx[k] / normAD[k]
+            u, v, r = split(sol.reshape(-1, rx[k + 1]), k, last)
+            x[k] = u.reshape(rx[k], *nm, r)
+            x[k + 1] = np.tensordot(v, x[k + 1], axes=([1], [0]))
+            nrm = np.linalg.norm(x[k + 1])
+            normx[k] *= nrm
+            x[k + 1] = x[k + 1] / nrm
+            rx[k + 1] = r
+            G[k + 1] = np.einsum("rab,amkA,bknB,rmnR->RAB", G[k], A[k], D4[k], x[k], optimize="greedy")
+            nrm = np.linalg.norm(G[k + 1])
+            nrm = nrm if nrm > 0 else 1.0
+            G[k + 1] = G[k + 1] / nrm
+            normAD[k] = nrm
+            nrmsc *= normAD[k] / normx[k]
+        if trace is not None:
+            trace.append(("fwd", swp, float(st["max_res"]), [int(q) for q in rx]))
+        if last:
+            break
+        if st["max_res"] < tol:
+            last = True
+    scale = np.exp(np.sum(np.log(normx)) / d)
+    return [scale * (c[:, :, 0] if vec else c) for c in x]
+
+
+def tt_approx_mat_mat_mul(A, D, x0=None, kick_rank=None, nswp=50, tol=1e-6, trace=None):
+    """src/tt_als.py:1502-1628."""
+    return _als_fit_product(A, D, x0, kick_rank, nswp, tol, trace)
+
+
+def tt_approx_mat_vec_mul(A, d_vec, x0=None, kick_rank=None, nswp=50, tol=1e-6, trace=None):
+    """src/tt_als.py:1637-1762."""
+    return _als_fit_product(A, d_vec, x0, kick_rank, nswp, tol, trace)
+
+
+def tt_random_gaussian(target_ranks, shape=(2,)):
+    """cy_src/tt_ops_cy.pyx:529-533."""
+    rr = [1] + list(target_ranks) + [1]
+    return tt_normalise([np.divide(1, a * np.prod(shape) * b) * np.random.randn(a, *shape, b)
+                         for a, b in zip(rr[:-1], rr[1:])])
+
+
 def tt_mat_vec_mul(mat, vec, op_tol, eps):
-    """src/tt_als.py:1765-1768, exact branch only (ALS fitting is SURVEY 8f-2)."""
-    if np.max(np.array(tt_ranks(mat)) * np.array(tt_ranks(vec))) > 80:
-        raise NotImplementedError("ALS mat-vec (src/tt_als.py:1637-1762) is out of scope (SURVEY 8f-2)")
-    return tt_rank_reduce(tt_fast_matrix_vec_mul(mat, vec, eps), op_tol)
+    """src/tt_als.py:1765-1768."""
+    if np.max(np.array(tt_ranks(mat)) * np.array(tt_ranks(vec))) <= 80:
+        return tt_rank_reduce(tt_fast_matrix_vec_mul(mat, vec, eps), op_tol)
+    return tt_approx_mat_vec_mul(mat, vec, tol=op_tol)
 
 
 def tt_mat_mat_mul(a, b, op_tol, eps):
-    """src/tt_als.py:1631-1634, exact branch only."""
-    if np.max(np.array(tt_ranks(a)) * np.array(tt_ranks(b))) > 40:
-        raise NotImplementedError("ALS mat-mat (src/tt_als.py:1502-1628) is out of scope (SURVEY 8f-2)")
-    return tt_rank_reduce(tt_fast_mat_mat_mul(a, b, eps), eps=op_tol)
+    """src/tt_als.py:1631-1634."""
+    if np.max(np.array(tt_ranks(a)) * np.array(tt_ranks(b))) <= 40:
+        return tt_rank_reduce(tt_fast_mat_mat_mul(a, b, eps), eps=op_tol)
+    return tt_approx_mat_mat_mul(a, b, tol=op_tol)
 
 
 def tt_IkronM(M):

@@ -335,29 +335,25 @@ def tt_random_gaussian(target_ranks, shape=(2,)):
 
 
 def tt_mat_vec_mul(mat, vec, op_tol, eps, verbose=False):
-    """src/tt_als.py:1765-1768: exact zip-up product rounded to op_tol.
-
-    The reference switches to an ALS fit of the product (tt_approx_mat_vec_mul, src/tt_als.py:1637-1762)
-    when a rank product exceeds 80.  That fit is not built yet; above the threshold the device path still forms the
-    exact zip-up product and rounds it to the same tolerance op_tol -- the same accuracy contract (the ALS fit targets
-    tol = op_tol), more work, and a different but equally valid TT representation of the result."""
-    if _all_rank_one_product(mat, vec):
-        return tt_rank_reduce(tt_fast_matrix_vec_mul(mat, vec, eps), op_tol)
-    rt = get_runtime()
-    dev = tt_fast_matrix_vec_mul_dev(_up(mat, rt), _up(vec, rt), eps, rt)
-    return _round_dev_to_host(dev, op_tol, rt)
+    """src/tt_als.py:1765-1768: exact zip-up product rounded to op_tol while every rank product is <= 80, otherwise the
+    ALS fit of the product (als_product.tt_approx_mat_vec_mul, which draws from the global NumPy RNG like the
+    reference's)."""
+    if np.max(np.array(tt_ranks(mat)) * np.array(tt_ranks(vec))) <= 80:
+        rt = get_runtime()
+        dev = tt_fast_matrix_vec_mul_dev(_up(mat, rt), _up(vec, rt), eps, rt)
+        return _round_dev_to_host(dev, op_tol, rt)
+    from .als_product import tt_approx_mat_vec_mul
+    return tt_approx_mat_vec_mul(mat, vec, tol=op_tol, verbose=verbose)
 
 
 def tt_mat_mat_mul(mat1, mat2, op_tol, eps, verbose=False):
-    """src/tt_als.py:1631-1634: exact zip-up product rounded to op_tol; above a rank product of 40 the reference fits the
-    product by ALS instead (tt_approx_mat_mat_mul, src/tt_als.py:1502-1628) -- see tt_mat_vec_mul."""
-    rt = get_runtime()
-    dev = tt_fast_mat_mat_mul_dev(_up(mat1, rt), _up(mat2, rt), eps, rt)
-    return _round_dev_to_host(dev, op_tol, rt)
-
-
-def _all_rank_one_product(a, b):
-    return False
+    """src/tt_als.py:1631-1634: exact zip-up product rounded to op_tol up to a rank product of 40, ALS fit above."""
+    if np.max(np.array(tt_ranks(mat1)) * np.array(tt_ranks(mat2))) <= 40:
+        rt = get_runtime()
+        dev = tt_fast_mat_mat_mul_dev(_up(mat1, rt), _up(mat2, rt), eps, rt)
+        return _round_dev_to_host(dev, op_tol, rt)
+    from .als_product import tt_approx_mat_mat_mul
+    return tt_approx_mat_mat_mul(mat1, mat2, tol=op_tol, verbose=verbose)
 
 
 def _round_dev_to_host(dev, eps, rt):

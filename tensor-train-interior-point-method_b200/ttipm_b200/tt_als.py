@@ -13,7 +13,9 @@ from . import kernels as K
 from . import tt as T
 from .amen import DeviceBlockAmen, NativeBlockAmen
 from .runtime import get_runtime
+from .als_product import tt_approx_mat_mat_mul, tt_approx_mat_vec_mul  # noqa: F401  (reference src/tt_als.py:1502,1637)
 from .tt import tt_mat_mat_mul, tt_mat_vec_mul  # noqa: F401  (re-exported, reference src/tt_als.py:1631,1765)
+from .tt_ops import cached_einsum  # noqa: F401  (reference src/tt_als.py imports it from src.tt_ops)
 
 
 def _tt_get_block(i, block_matrix_tt):
@@ -228,6 +230,13 @@ class TTBlockMatrixView:
 
     def rcompressed_block_local_product(self, XAX_k, ZAX_kp1, x_core, shape):
         return self._product(XAX_k, ZAX_kp1, x_core, shape, False, True)
+
+
+def truncated_svd(matrix, trunc_rank):
+    """reference src/tt_als.py:269-274: leading trunc_rank left singular vectors and the matching rows of S V^T."""
+    rt = get_runtime()
+    U, _, W = K.svd_left(rt.to_device(matrix), rt=rt)
+    return rt.to_host(U[:, :trunc_rank]), rt.to_host(W[:trunc_rank])
 
 
 # ---- interface updates on NumPy operands (reference src/tt_als.py:252-265) --------------------------

@@ -11,6 +11,7 @@ import scipy.linalg  # noqa: F401
 import scipy.sparse  # noqa: F401
 import scipy.sparse.linalg  # noqa: F401
 
+from .als_product import add_kick_rank, symmetric_powers_of_two  # noqa: F401  (cy_src/tt_ops_cy.pyx:538-579)
 from .lgmres import IneqMatVecWrapper, MatVecWrapper  # noqa: F401
 from .tt import (prune_singular_vals, tt_add, tt_diag, tt_diag_op, tt_diagonal, tt_entrywise_sum,  # noqa: F401
                  tt_fast_hadamard, tt_fast_mat_mat_mul, tt_fast_matrix_vec_mul, tt_identity, tt_IkronM,

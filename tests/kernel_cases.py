@@ -411,3 +411,29 @@ def case_tt_algebra(rt):
         errs["prune"] = float(np.abs(np.array([T.prune_singular_vals(z["tt/prune_s"], e) for e in z["tt/prune_eps"]])
                                      - z["tt/prune_out"]).max())
     return errs
+
+
+ALS_CASES = ("matvec_d5", "matmat_d4", "matmat_d5", "matvec_d6")
+
+
+def case_als_products(rt, names=ALS_CASES):
+    """Device ALS fit of a TT product (ttipm_b200.als_product) vs the reference's own results
+    (tests/golden/als_products.npz, written by oracle/ref_harness/make_golden.py als) on the same inputs and the same
+    NumPy seed, and vs the oracle restatement: identical ranks and number of half sweeps, dense product to 1e-10."""
+    from ttipm_b200 import als_product as AP, use_runtime
+    z = G.load("als_products.npz")
+    errs = {}
+    cp = lambda tt: [c.copy() for c in tt]
+    for name in names:
+        A, D, ref = (G.get_tt(z, f"{name}/{q}") for q in ("A", "D", "out"))
+        tol = float(z[name + "/tol"])
+        tr_dev, tr_orc = [], []
+        np.random.seed(int(z[name + "/seed"]))
+        with use_runtime(rt):
+            mine = AP.als_fit_product(cp(A), cp(D), tol=tol, trace=tr_dev)
+        np.random.seed(int(z[name + "/seed"]))
+        (O.tt_approx_mat_vec_mul if D[0].ndim == 3 else O.tt_approx_mat_mat_mul)(cp(A), cp(D), tol=tol, trace=tr_orc)
+        errs[name + "_shape"] = 0.0 if [c.shape for c in mine] == [c.shape for c in ref] else 1.0
+        errs[name + "_sweeps"] = 0.0 if [(t[0], t[1], t[3]) for t in tr_dev] == [(t[0], t[1], t[3]) for t in tr_orc] else 1.0
+        errs[name] = rel(_dense_tt(mine), _dense_tt(ref))
+    return errs

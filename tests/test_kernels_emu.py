@@ -129,7 +129,7 @@ def test_tt_algebra(rt):
 
 def test_tt_products_above_als_threshold(rt):
     """rank products above the reference's ALS thresholds (80 mat-vec / 40 mat-mat, src/tt_als.py:1632,1766): the
-    dispatchers form the exact zip-up product and round to op_tol -- dense results agree with NumPy to that tolerance"""
+    dispatchers take the ALS fit like the reference's; the dense result agrees with NumPy to the fit tolerance"""
     import numpy as np
     from ttipm_b200 import tt as T, use_runtime
     rng = np.random.default_rng(3)
@@ -143,6 +143,7 @@ def test_tt_products_above_als_threshold(rt):
     rm, rv = 9, 10                                                # 90 > 80
     mat = [rng.standard_normal((1, 4, 4, rm)), rng.standard_normal((rm, 4, 4, 1))]
     vec = [rng.standard_normal((1, 4, rv)), rng.standard_normal((rv, 4, 1))]
+    np.random.seed(5)
     with use_runtime(rt):
         out = T.tt_mat_vec_mul(mat, vec, 1e-10, 1e-12)
     want = np.einsum("imjn,mn->ij", dense(mat), dense(vec))      # cores (1, i, m, r), (r, j, n, 1)
@@ -155,3 +156,31 @@ def test_tt_products_above_als_threshold(rt):
     B = dense(m2)
     want2 = np.einsum("imjn,mpnq->ipjq", A, B)
     assert np.linalg.norm(dense(out2) - want2) <= 1e-8 * np.linalg.norm(want2)
+
+
+def test_als_products_vs_reference(rt):
+    """ALS-fitted products against the reference's own outputs; the d = 6 case runs in the GPU tier"""
+    KC.assert_small(KC.case_als_products(rt, KC.ALS_CASES[:3]))
+
+
+def test_truncated_svd_and_kick_rank(rt):
+    """reference src/tt_als.py:269-274 and cy_src/tt_ops_cy.pyx:538-579 through the device QR / SVD"""
+    import numpy as np
+    from ttipm_b200 import tt_als, tt_ops, use_runtime
+    rng = np.random.default_rng(8)
+    Mx = rng.standard_normal((12, 7))
+    with use_runtime(rt):
+        u, sv = tt_als.truncated_svd(Mx.copy(), 3)
+        U, s, Vt = np.linalg.svd(Mx, full_matrices=False)
+        assert u.shape == (12, 3) and sv.shape == (3, 7)
+        assert np.linalg.norm(u @ sv - (U[:, :3] * s[:3]) @ Vt[:3]) <= 1e-12 * np.linalg.norm(Mx)
+        np.random.seed(4)
+        q, w, r = tt_ops.add_kick_rank(U[:, :3].copy(), (s[:3, None] * Vt[:3]).copy(), 2)
+    np.random.seed(4)
+    O = KC.O
+    qo, wo, ro = O.add_kick_rank(U[:, :3].copy(), (s[:3, None] * Vt[:3]).copy(), 2)
+    assert r == ro == 5 and np.linalg.norm(q.T @ q - np.eye(5)) <= 1e-13
+    assert np.linalg.norm(q @ w - qo @ wo) <= 1e-12 * np.linalg.norm(qo @ wo)
+    assert np.linalg.norm(q @ q.T - qo @ qo.T) <= 1e-12
+    assert list(tt_ops.symmetric_powers_of_two(5)) == list(O.symmetric_powers_of_two(5)) == [2, 4, 8, 4, 2]
+    assert list(tt_ops.symmetric_powers_of_two(4)) == [2, 4, 4, 2]

@@ -144,3 +144,9 @@ def test_elementwise(rt):
 
 def test_tt_algebra(rt):
     KC.assert_small(KC.case_tt_algebra(rt))
+
+
+def test_als_products_vs_reference(rt):
+    """ALS-fitted TT products (reference src/tt_als.py:1502-1762) on the device against the reference's own
+    outputs on the same inputs and NumPy seed: same ranks, same half sweeps as the oracle, dense product to 1e-10"""
+    KC.assert_small(KC.case_als_products(rt))
