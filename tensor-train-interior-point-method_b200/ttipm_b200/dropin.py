@@ -17,7 +17,8 @@ TT_OPS = ["tt_add", "tt_sub", "tt_scale", "tt_inner_prod", "tt_norm", "tt_normal
           "tt_psd_rank_reduce", "tt_mask_rank_reduce", "tt_rl_orthogonalise", "tt_fast_matrix_vec_mul",
           "tt_fast_mat_mat_mul", "tt_fast_hadamard", "tt_IkronM", "tt_MkronI", "tt_diag", "tt_diag_op",
           "tt_entrywise_sum", "tt_rank_retraction", "tt_rl_orthogonalise_py", "tt_sum", "prune_singular_vals"]
-TT_ALS = ["tt_restarted_block_amen", "tt_block_amen", "tt_mat_vec_mul", "tt_mat_mat_mul", "TTBlockMatrix",
+TT_ALS = ["tt_restarted_block_amen", "tt_block_amen", "tt_mat_vec_mul", "tt_mat_mat_mul", "tt_approx_mat_vec_mul",
+          "tt_approx_mat_mat_mul", "TTBlockMatrix",
           "TTBlockVector", "compute_phi_bck_A", "compute_phi_fwd_A", "compute_phi_bck_rhs", "compute_phi_fwd_rhs"]
 LGMRES = ["MatVecWrapper", "IneqMatVecWrapper"]
 
