@@ -41,6 +41,8 @@ def main():
         if "--profile" in sys.argv:
             pr.disable()
             pstats.Stats(pr).sort_stats("cumulative").print_stats(70)
+    from ttipm_b200 import als_product
+    out["dropin"]["als_product_fits"] = dict(als_product.STATS)
     print("DROPIN", json.dumps(out["dropin"]), flush=True)
     for i, a in enumerate(sys.argv):
         if a == "--out":

@@ -19,6 +19,8 @@ import numpy as np
 from . import kernels as K
 from .runtime import get_runtime
 
+STATS = {"fits": 0, "half_sweeps": 0}       # process-wide counters (end-to-end harness, tools)
+
 
 def symmetric_powers_of_two(length):
     """cy_src/tt_ops_cy.pyx:538-555."""
@@ -129,6 +131,7 @@ def als_fit_product(A, D, x0=None, kick_rank=None, nswp=50, tol=1e-6, verbose=Fa
     """NumPy cores in, NumPy cores out; same arguments and RNG draws as the reference's two functions."""
     from .tt import tt_random_gaussian, tt_ranks
     rt = get_runtime()
+    STATS["fits"] += 1
     vec = D[0].ndim == 3
     if x0 is None:
         max_ranks = np.maximum((np.array(tt_ranks(A)) + np.array(tt_ranks(D))) / 2, 2).astype(int)
@@ -181,6 +184,7 @@ def als_fit_product(A, D, x0=None, kick_rank=None, nswp=50, tol=1e-6, verbose=Fa
             G[k] = K.ewise(Gk, 1.0 / nrm, rt=rt)
             normAD[k - 1] = nrm
             nrmsc *= normAD[k - 1] / normx[k - 1]
+        STATS["half_sweeps"] += 1
         if trace is not None:
             trace.append(("bck", swp, float(max_res), list(rx)))
         if last:
@@ -207,6 +211,7 @@ def als_fit_product(A, D, x0=None, kick_rank=None, nswp=50, tol=1e-6, verbose=Fa
             G[k + 1] = K.ewise(Gk, 1.0 / nrm, rt=rt)
             normAD[k] = nrm
             nrmsc *= normAD[k] / normx[k]
+        STATS["half_sweeps"] += 1
         if trace is not None:
             trace.append(("fwd", swp, float(max_res), list(rx)))
         if last:
