@@ -150,3 +150,30 @@ def test_als_products_vs_reference(rt):
     """ALS-fitted TT products (reference src/tt_als.py:1502-1762) on the device against the reference's own
     outputs on the same inputs and NumPy seed: same ranks, same half sweeps as the oracle, dense product to 1e-10"""
     KC.assert_small(KC.case_als_products(rt))
+
+
+def test_als_product_dispatch_large_ranks(rt):
+    """size-independent property at ranks the CPU tier cannot afford: a mat-vec whose rank products (96) exceed the
+    reference's threshold of 80 goes through the ALS fit (src/tt_als.py:1765-1768) and must reproduce the exact product
+    (dense NumPy contraction of the same trains) to the fit tolerance, with bond ranks no larger than the exact ones"""
+    import numpy as np
+    from ttipm_b200 import als_product as AP, tt as T, use_runtime
+    rng = np.random.default_rng(12)
+    d, n = 8, 4
+    ra, rd = [1, 4, 6, 6, 6, 6, 6, 4, 1], [1, 8, 16, 16, 16, 16, 16, 8, 1]
+    A = [rng.standard_normal((ra[k], n, n, ra[k + 1])) / np.sqrt(ra[k] * ra[k + 1]) for k in range(d)]
+    v = [rng.standard_normal((rd[k], n, rd[k + 1])) / np.sqrt(rd[k] * rd[k + 1]) for k in range(d)]
+    fits = AP.STATS["fits"]
+    np.random.seed(21)
+    with use_runtime(rt):
+        out = T.tt_mat_vec_mul([c.copy() for c in A], [c.copy() for c in v], 1e-6, 1e-12)
+    assert AP.STATS["fits"] == fits + 1
+    # exact product, core by core: (a b, m, A B) = sum_k A[a, m, k, A'] v[b, k, B]
+    exact = [np.einsum("amkA,bkB->abmAB", a, b).reshape(a.shape[0] * b.shape[0], n, -1) for a, b in zip(A, v)]
+    dense = lambda tt: KC._dense_tt(tt)
+    want = dense(exact)
+    got = dense(out)
+    assert got.shape == want.shape
+    assert np.linalg.norm(got - want) <= 1e-6 * np.linalg.norm(want)
+    caps = [min(4 ** (k + 1), 4 ** (d - 1 - k), ra[k + 1] * rd[k + 1]) for k in range(d - 1)]
+    assert all(c.shape[-1] <= cap for c, cap in zip(out[:-1], caps))
