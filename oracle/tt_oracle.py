@@ -582,7 +582,9 @@ def _als_fit_product(A, D, x0, kick_rank, nswp, tol, trace=None):
 
     State as in the reference: unit-norm interfaces G[k] (r, a, b) with their norms in
     normAD, unit-norm non-orthogonal neighbour cores with their norms in normx, and the
-    running scale nrmsc that converts a raw local contraction into the local solution."""
+    running scale nrmsc that converts a raw local contraction into the local solution.
+    The three 4-operand contractions are explicit pairwise tensordot chains (BLAS), which is what
+    opt_einsum does for the reference; np.einsum's greedy path falls back to its non-BLAS loop here."""
     vec = D[0].ndim == 3
     D4 = [c.reshape(c.shape[0], c.shape[1], 1, c.shape[2]) for c in D] if vec else D
     if x0 is None:
@@ -601,7 +603,9 @@ def _als_fit_product(A, D, x0, kick_rank, nswp, tol, trace=None):
     st = {"max_res": 0.0}
 
     def local(k):
-        sol = np.einsum("rab,amkA,bknB,RAB->rmnR", G[k], A[k], D4[k], G[k + 1], optimize="greedy") * nrmsc
+        t = np.tensordot(G[k], D4[k], axes=([2], [0]))                       # 'rab,amkA,bknB,RAB->rmnR'
+        t = np.tensordot(t, A[k], axes=([1, 2], [0, 2]))                     # (r, n, B, m, A')
+        sol = np.tensordot(t, G[k + 1], axes=([4, 2], [1, 2])).transpose(0, 2, 1, 3) * nrmsc
         res = np.linalg.norm(sol - x[k]) / max(np.linalg.norm(sol), 1e-8)
         st["max_res"] = max(st["max_res"], res)
         return sol
@@ -631,7 +635,9 @@ def _als_fit_product(A, D, x0, kick_rank, nswp, tol, trace=None):
             normx[k - 1] *= nrm
             x[k - 1] = x[k - 1] / nrm
             rx[k] = r
-            G[k] = np.einsum("RAB,amkA,bknB,rmnR->rab", G[k + 1], A[k], D4[k], x[k], optimize="greedy")
+            t = np.tensordot(x[k], G[k + 1], axes=([3], [0]))                # 'RAB,amkA,bknB,rmnR->rab'
+            t = np.tensordot(t, D4[k], axes=([2, 4], [2, 3]))                # (r, m, A', b, k)
+            G[k] = np.tensordot(t, A[k], axes=([1, 2, 4], [1, 3, 2])).transpose(0, 2, 1)
             nrm = np.linalg.norm(G[k])
             nrm = nrm if nrm > 0 else 1.0
             G[k] = G[k] / nrm
@@ -658,7 +664,9 @@ def _als_fit_product(A, D, x0, kick_rank, nswp, tol, trace=None):
             normx[k] *= nrm
             x[k + 1] = x[k + 1] / nrm
             rx[k + 1] = r
-            G[k + 1] = np.einsum("rab,amkA,bknB,rmnR->RAB", G[k], A[k], D4[k], x[k], optimize="greedy")
+            t = np.tensordot(G[k], x[k], axes=([0], [0]))                    # 'rab,amkA,bknB,rmnR->RAB'
+            t = np.tensordot(t, A[k], axes=([0, 2], [0, 1]))                 # (b, n, R, k, A')
+            G[k + 1] = np.tensordot(t, D4[k], axes=([0, 1, 3], [0, 2, 1]))
             nrm = np.linalg.norm(G[k + 1])
             nrm = nrm if nrm > 0 else 1.0
             G[k + 1] = G[k + 1] / nrm
