@@ -7,6 +7,7 @@ does not.
   python oracle/ref_harness/make_golden.py amen maxcut 5 1 319 0,1,5 [--budget 600]
   python oracle/ref_harness/make_golden.py e2e maxcut 5 1 319
   python oracle/ref_harness/make_golden.py als
+  python oracle/ref_harness/make_golden.py eigen maxcut 5 1 319 0,1,4,9
 
 File formats (all float64 unless noted):
   kernels_*.npz : flat dict "case/<name>/in_*", ".../out_*"
@@ -346,6 +347,65 @@ def amen(problem, dim, rank, seed, which, budget_s, local=False, inputs_only=Fal
     print("AMEn calls seen:", counter[0])
 
 
+def eigen(problem, dim, rank, seed, which):
+    """Trace calls of the step-size eigen sweeps (reference src/tt_als.py:1132-1283 tt_max_generalised_eigen,
+    :1392-1499 tt_min_eig) made by the reference IPM.  eigen_<cfg>_<n>.npz: "kind" (0 = generalised,
+    1 = min_eig), "A/<k>", "Delta/<k>" (generalised only), "x0/<k>" (absent if None), "tol", rng_keys / rng_pos at
+    entry, "out_scalar" (step size / eigenvalue), "out/x/<k>"."""
+    ref = ref_env.load()
+    ipm = ref.tt_ipm
+    cfg = load_config(problem, dim)
+    obj_tt, L_op_tt, bias_tt, ineq_mask, lag_maps = build_problem(ref, problem, dim, rank, seed)
+    tag = f"{problem}_{dim}_r{rank}_s{seed}"
+    counter = [0]
+    orig_gen, orig_min = ipm.tt_max_generalised_eigen, ipm.tt_min_eig
+
+    def record(kind, A, Delta, x0, tol, call):
+        idx = counter[0]
+        counter[0] += 1
+        if idx not in which:
+            res = call()
+            if idx > max(which):
+                raise _Budget()
+            return res
+        out = {"kind": np.array(kind), "tol": np.array(tol)}
+        _put_tt(out, "A", _cp(A))
+        if Delta is not None:
+            _put_tt(out, "Delta", _cp(Delta))
+        if x0 is not None:
+            _put_tt(out, "x0", _cp(x0))
+        st = np.random.get_state()
+        out["rng_keys"], out["rng_pos"] = np.array(st[1]), np.array(st[2])
+        res = call()
+        scalar, xs = (res[0], res[1]) if kind == 0 else (res[1], res[0])
+        out["out_scalar"] = np.array(np.nan if scalar is None else scalar, dtype=np.float64)
+        _put_tt(out, "out/x", _cp(xs))
+        path = os.path.join(GOLD, f"eigen_{tag}_{idx}.npz")
+        np.savez_compressed(path, **out)
+        print(f"wrote {path} kind={kind} scalar={out['out_scalar']} ({os.path.getsize(path) / 1e3:.0f} kB)", flush=True)
+        return res
+
+    def traced_gen(A, Delta, x0=None, nswp=10, tol=1e-8, size_limit=256, verbose=False):
+        return record(0, A, Delta, x0, tol, lambda: orig_gen(A, Delta, x0=x0, nswp=nswp, tol=tol,
+                                                              size_limit=size_limit, verbose=verbose))
+
+    def traced_min(A, x0=None, nswp=10, tol=1e-8, size_limit=64, return_eig_val=False, verbose=False):
+        return record(1, A, None, x0, tol, lambda: orig_min(A, x0=x0, nswp=nswp, tol=tol, size_limit=size_limit,
+                                                            return_eig_val=return_eig_val, verbose=verbose))
+
+    ipm.tt_max_generalised_eigen, ipm.tt_min_eig = traced_gen, traced_min
+    try:
+        ipm.tt_ipm(lag_maps, obj_tt, L_op_tt, bias_tt, ineq_mask=ineq_mask, max_iter=cfg["max_iter"], verbose=False,
+                   gap_tol=float(cfg["gap_tol"]), op_tol=float(cfg["op_tol"]), warm_up=cfg["warm_up"],
+                   abs_tol=float(cfg["abs_tol"]), aho_direction=False, mals_restarts=cfg["mals_restarts"],
+                   max_refinement=cfg["max_refinement"], lambdaStar=float(cfg.get("lambdaStar", 1)),
+                   lambdaStarIneq=float(cfg.get("lambdaStarIneq", 1)))
+    except _Budget:
+        pass
+    finally:
+        ipm.tt_max_generalised_eigen, ipm.tt_min_eig = orig_gen, orig_min
+
+
 def e2e(problem, dim, rank, seed):
     from run_ref_ipm import run
     res = run(problem, dim, rank, seed, verbose=False)
@@ -369,5 +429,8 @@ if __name__ == "__main__":
              inputs_only="--inputs-only" in sys.argv)
     elif cmd == "als":
         als()
+    elif cmd == "eigen":
+        eigen(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]),
+              set(int(v) for v in sys.argv[6].split(",")))
     elif cmd == "e2e":
         e2e(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
