@@ -138,9 +138,13 @@ int ttipm_local_lgmres(int ineq, const ttipm_term* K00, const ttipm_term* K01, c
 
 /* ---- dense factorisations of core unfoldings ------------------------------------------------- */
 /* One kernel serves every shape (csrc/linalg.cu): a single matrix with min(M, N) >= the threshold below runs as one
- * cooperative multi-CTA launch (panel Householder QR + QR-preconditioned block one-sided Jacobi); smaller or batched
+ * multi-CTA launch (panel Householder QR + QR-preconditioned block one-sided Jacobi); smaller or batched
  * matrices use one CTA per matrix.  The setter returns the previous threshold (default 17); min_dim <= 0 only queries. */
 int ttipm_linalg_coop_min_dim(int min_dim);
+/* The multi-CTA launch is one thread-block cluster of up to 16 CTAs (hardware cluster barrier between phases): 1
+ * (default) / 0 = cooperative launch with a software grid barrier.  Returns the previous setting; a negative argument
+ * only queries. */
+int ttipm_linalg_use_cluster(int on);
 
 /* Threads per CTA of the QR / SVD kernel (256 or 512; tuning hook).  Returns the previous value; any other argument
  * only queries. */

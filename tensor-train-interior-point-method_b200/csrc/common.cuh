@@ -114,6 +114,59 @@ TT_DEV void grid_sync(unsigned* counter, unsigned& epoch) {
 }
 
 // ---------------------------------------------------------------------------
+// thread-block cluster barrier (hardware; release/acquire at cluster scope, so global and distributed shared
+// memory written before the barrier is visible to every CTA of the cluster after it).  All threads of every
+// CTA of the cluster must call it.
+// ---------------------------------------------------------------------------
+#ifndef TTIPM_EMU
+TT_DEV void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+#else
+TT_DEV void cluster_sync_all() { emu_cluster_sync_impl(); }
+#endif
+
+// ---------------------------------------------------------------------------
+// 1-D bulk asynchronous copies (TMA engine, SASS UBLKCP) global -> shared with an mbarrier that counts the
+// bytes landed (SASS SYNCS).  Addresses and sizes are multiples of 16 bytes.  One thread issues, every thread
+// that reads the data waits on the barrier's phase parity.  Under the CPU emulator the issuing thread copies
+// synchronously and the wait is a block barrier.
+// ---------------------------------------------------------------------------
+#ifndef TTIPM_EMU
+TT_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+TT_DEV void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+TT_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+TT_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+TT_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// orders generic-proxy accesses (ld/st) against async-proxy accesses (bulk copies) of the same memory
+TT_DEV void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#else
+TT_DEV void mbar_init(unsigned long long*, unsigned) {}
+TT_DEV void mbar_expect_tx(unsigned long long*, unsigned) {}
+TT_DEV void mbar_wait(unsigned long long*, unsigned) { __syncthreads(); }
+TT_DEV void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+TT_DEV void fence_proxy_async() {}
+#endif
+
+// ---------------------------------------------------------------------------
 // tgemm:  C(m, n) = sum_k A(m, k) * B(k, n)   for m < M, n < N, k < K
 //   A element = A[axoff(aM, m) + axoff(aK, k)],  B element = B[axoff(bK, k) + axoff(bN, n)]
 //   store(m, n, value) is called exactly once per output element.
@@ -230,6 +283,85 @@ TT_HD int imax(int a, int b) { return a > b ? a : b; }
 // ---------------------------------------------------------------------------
 // launch helper: every kernel takes ONE parameter struct by value
 // ---------------------------------------------------------------------------
+#ifndef TTIPM_EMU
+// largest shared-memory opt-in of the device, cached
+static inline int smem_optin_max() {
+    static int optin_max = 0;
+    if (!optin_max) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    return optin_max;
+}
+#endif
+
+// Can `grid_x` CTAs (grid = ONE thread-block cluster along x, times grid_y independent clusters) be launched?
+template <class P>
+bool cluster_launch_possible(void (*kern)(P), int grid_x, int grid_y, dim3 block, size_t smem) {
+#ifdef TTIPM_EMU
+    (void)kern; (void)grid_x; (void)grid_y; (void)block; (void)smem;
+    return true;
+#else
+    if (grid_x > 16) return false;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_optin_max() > (int)smem ? smem_optin_max() : (int)smem);
+    if (grid_x > 8 && cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid_x, grid_y);
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = grid_x;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, (const void*)kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return n >= 1;
+#endif
+}
+
+// launch with grid.x CTAs forming one thread-block cluster (grid.y independent clusters)
+template <class P>
+int launch_kernel_cluster(const char* name, void (*kern)(P), dim3 grid, dim3 block, size_t smem, tt_stream_t st,
+                          const P& params) {
+#ifdef TTIPM_EMU
+    (void)name;
+    (void)st;
+    ::emu::launch(grid, block, smem, true, [&]() { kern(params); });
+    return 0;
+#else
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = grid.x;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, params);
+    if (e != cudaSuccess) {
+        set_error("%s: cluster launch (%u CTAs) failed: %s", name, grid.x, cudaGetErrorString(e));
+        return 3;
+    }
+    return 0;
+#endif
+}
+
 template <class P>
 int launch_kernel(const char* name, void (*kern)(P), dim3 grid, dim3 block, size_t smem, tt_stream_t st, bool coop,
                   const P& params) {

@@ -34,6 +34,10 @@ struct Dim3 {
 struct Barrier {
     unsigned n = 0, count = 0, gen = 0;
 };
+struct ClusterBar {          // one per thread-block cluster of a launch (CTAs sharing blockIdx.y/z)
+    std::atomic<unsigned> count{0}, gen{0};
+    unsigned n = 1;
+};
 struct Fiber {
     ucontext_t ctx;
     char* stack = nullptr;
@@ -49,6 +53,7 @@ struct Cta {
     int current = 0;
     Dim3 grid, block, bidx;
     const std::function<void()>* body = nullptr;
+    ClusterBar* cbar = nullptr;
 };
 extern thread_local Dim3 threadIdx_, blockIdx_, blockDim_, gridDim_;
 extern thread_local Cta* cta;
@@ -73,7 +78,8 @@ inline void fiber_entry() {
     swapcontext(&c->fibers[c->current].ctx, &c->sched);
 }
 
-inline void run_cta(Dim3 grid, Dim3 block, size_t smem, Dim3 bidx, const std::function<void()>& body) {
+inline void run_cta(Dim3 grid, Dim3 block, size_t smem, Dim3 bidx, const std::function<void()>& body,
+                    ClusterBar* cbar = nullptr) {
     const unsigned nt = block.x, nw = (nt + 31) / 32;
     const size_t stack_bytes = 256 * 1024;
     Cta c;
@@ -85,6 +91,7 @@ inline void run_cta(Dim3 grid, Dim3 block, size_t smem, Dim3 bidx, const std::fu
     c.smem = (unsigned char*)aligned_alloc(64, ((smem + 63) / 64 + 1) * 64);
     memset(c.smem, 0xCD, smem);   // poison: uninitialised shared memory reads show up
     c.grid = grid; c.block = block; c.bidx = bidx; c.body = &body;
+    c.cbar = cbar;
     c.fibers.resize(nt);
     cta = &c;
     blockIdx_ = bidx; blockDim_ = block; gridDim_ = grid;
@@ -116,13 +123,16 @@ inline void run_cta(Dim3 grid, Dim3 block, size_t smem, Dim3 bidx, const std::fu
 // concurrent = all CTAs alive at once (needed by kernels that use grid_sync)
 inline void launch(Dim3 grid, Dim3 block, size_t smem, bool concurrent, const std::function<void()>& body) {
     std::vector<std::thread> pool;
+    std::vector<ClusterBar> cbars(grid.y * grid.z);
+    for (auto& cb : cbars) cb.n = grid.x;
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
+                ClusterBar* cb = &cbars[bz * grid.y + by];
                 if (concurrent && grid.x * grid.y * grid.z > 1)
-                    pool.emplace_back([=, &body]() { run_cta(grid, block, smem, Dim3(bx, by, bz), body); });
+                    pool.emplace_back([=, &body]() { run_cta(grid, block, smem, Dim3(bx, by, bz), body, cb); });
                 else
-                    run_cta(grid, block, smem, Dim3(bx, by, bz), body);
+                    run_cta(grid, block, smem, Dim3(bx, by, bz), body, cb);
             }
     for (auto& th : pool) th.join();
 }
@@ -135,6 +145,21 @@ typedef ::emu::Dim3 dim3;
 #define gridDim (::emu::gridDim_)
 
 static inline void __syncthreads() { ::emu::barrier_wait(::emu::cta->bar); }
+// thread-block cluster barrier: the CTAs sharing blockIdx.y/z of a concurrent launch (a lone CTA: block barrier)
+static inline void emu_cluster_sync_impl() {
+    ::emu::barrier_wait(::emu::cta->bar);
+    ::emu::ClusterBar* cb = ::emu::cta->cbar;
+    if (cb && cb->n > 1 && ::emu::threadIdx_.x == 0) {
+        const unsigned gen = cb->gen.load();
+        if (cb->count.fetch_add(1) + 1 == cb->n) {
+            cb->count.store(0);
+            cb->gen.fetch_add(1);
+        } else {
+            while (cb->gen.load() == gen) std::this_thread::yield();
+        }
+    }
+    ::emu::barrier_wait(::emu::cta->bar);
+}
 static inline void __syncwarp() { ::emu::barrier_wait(::emu::cta->wbar[::emu::cta->current >> 5]); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) {

@@ -28,6 +28,11 @@
 //           A CTA owns a pair of row blocks per round, keeps their rows of R and of the accumulator in shared
 //           memory and orthogonalises every cross pair (intra-block pairs once per sweep); block pairs follow
 //           a round-robin tournament with one grid barrier per round (K / nb rounds per sweep instead of K).
+//
+// Blackwell specifics: a multi-CTA launch is ONE thread-block cluster (<= 16 CTAs), so every phase boundary is the
+// hardware cluster barrier instead of an atomic counter in global memory; the rows [R | accumulator] of a Jacobi
+// block are contiguous in the workspace and arrive in shared memory as one bulk asynchronous copy per block
+// (cp.async.bulk + mbarrier), as do the columns of a reflector panel.
 #include "api_util.h"
 
 namespace ttipm {
@@ -57,6 +62,11 @@ struct LinParams {
     double floor_factor; // rows below floor_factor * eps * ||R||_F are left alone by the Jacobi iteration (0 = off)
     int ldp;             // panel leading dimension in shared memory
     int oOrd, oSvS, oTaus, oP;   // shared-memory offsets (doubles)
+    int oRows;           // shared-memory offset of the Jacobi rows (even)
+    int ld1;             // leading dimension of the column-major working copy W1 (even)
+    int ldk;             // leading dimension of the K x K factors W2, W3 (even)
+    int ldg;             // row stride of the Jacobi rows [R (K) | accumulator (Mj) | pad], global and shared (even)
+    int cluster;         // the grid is one thread-block cluster: hardware barrier between phases
     int nbatch;
 };
 
@@ -67,16 +77,32 @@ struct LinCtx {
     unsigned epoch;
     int lane, wid, nw, gw, GW;
     double* panel;       // TT_QR_PB reflector columns: shared memory, or global scratch for very tall matrices
+    unsigned long long* mbar;    // byte-counting barrier of the bulk copies (shared memory)
+    unsigned mphase;
+    bool bulk;           // panel in shared memory: bulk copies apply
     TT_DEVM LinCtx(const LinParams& pp, double* s, unsigned* bar) : p(pp), smem(s), barrier(bar), epoch(0) {
         panel = s + pp.oP;
+        mbar = (unsigned long long*)(s + 38);
+        mphase = 0;
+        bulk = pp.oPg < 0;
         lane = threadIdx.x & 31;
         wid = threadIdx.x >> 5;
         nw = blockDim.x >> 5;
         gw = blockIdx.x * nw + wid;
         GW = gridDim.x * nw;
     }
-    TT_DEVM void sync() { grid_sync(barrier, epoch); }
+    TT_DEVM void sync() {
+        if (p.cluster) cluster_sync_all();
+        else grid_sync(barrier, epoch);
+    }
 };
+
+// the kernel's dynamic shared memory, re-derived where it is used heavily so that the compiler keeps the
+// shared address space (LDS / STS instead of generic loads)
+TT_DEV double* lin_smem() {
+    TT_SMEM_DECL(lin_smem_raw);
+    return (double*)lin_smem_raw;
+}
 
 #ifndef TTIPM_EMU
 TT_DEV long long lin_now() {
@@ -91,22 +117,21 @@ TT_DEV double lin_rsqrt(double x) { return 1.0 / sqrt(x); }
 #endif
 
 // x <- (I - tj v v^T) x for a vector held in registers with the fixed mapping element i <-> (lane, q = i / 32);
-// v[j] = 1 implicit, v[i] given for j < i < len (v may point before its first valid element), zero above j
-TT_DEV void lin_reflect_reg(double (&reg)[TT_LIN_REG], const double* v, int j, int len, double tj, int lane) {
+// v[j] = 1 implicit, v[i] given for j < i < len (v may point before its first valid element), zero above j.
+// NQ = register chunks actually in use (32 * NQ >= len).
+template <int NQ>
+TT_DEV void lin_reflect_reg(double (&reg)[NQ], const double* v, int j, int len, double tj, int lane) {
     double d = 0.0;
+    double vv[NQ];
 #pragma unroll
-    for (int q = 0; q < TT_LIN_REG; ++q) {
+    for (int q = 0; q < NQ; ++q) {
         const int i = lane + 32 * q;
-        const double vv = (i > j && i < len) ? v[i] : (i == j ? 1.0 : 0.0);
-        d += vv * reg[q];
+        vv[q] = (i > j && i < len) ? v[i] : (i == j ? 1.0 : 0.0);
+        d += vv[q] * reg[q];
     }
     d = warp_sum(d) * tj;
 #pragma unroll
-    for (int q = 0; q < TT_LIN_REG; ++q) {
-        const int i = lane + 32 * q;
-        const double vv = (i > j && i < len) ? v[i] : (i == j ? 1.0 : 0.0);
-        reg[q] -= d * vv;
-    }
+    for (int q = 0; q < NQ; ++q) reg[q] -= d * vv[q];
 }
 // same for a vector in memory (len > 32 * TT_LIN_REG); element i at x[i * xs]; a thread only re-reads its own writes
 TT_DEV void lin_reflect_mem(double* x, long xs, const double* v, int j, int len, double tj, int lane) {
@@ -122,104 +147,137 @@ TT_DEV void lin_reflect_mem(double* x, long xs, const double* v, int j, int len,
     }
 }
 
-// stage reflectors [j0, j0 + pw) of W (column-major Mq x *, rows j0.. only) and their tau into shared memory
-TT_DEV void lin_load_panel(const double* W, const double* tau, int Mq, int j0, int pw, bool with_tau, double* P,
-                           double* taus, int ldp) {
+// stage reflectors [j0, j0 + pw) of W (column-major, leading dimension ld, rows j0..Mq-1 only) and their tau into the
+// panel P.  Shared-memory panels are filled by one bulk asynchronous copy per column; ends with the data visible to
+// every thread of the CTA.  Callers put a block barrier before the call (previous readers of P are done).
+TT_DEV void lin_load_panel(LinCtx& c, const double* W, const double* tau, int ld, int Mq, int j0, int pw, bool with_tau,
+                           double* P, double* taus, int ldp) {
     const int rows = Mq - j0;
+    if (with_tau && (int)threadIdx.x < pw) taus[threadIdx.x] = ld_cg(tau + j0 + threadIdx.x);
+    if (c.bulk) {
+        if (threadIdx.x == 0) {
+            const unsigned bytes = (unsigned)((rows + 1) & ~1) * 8u;       // ld and ldp are even: the pad element exists
+            fence_proxy_async();
+            mbar_expect_tx(c.mbar, bytes * (unsigned)pw);
+            for (int j = 0; j < pw; ++j) bulk_g2s(P + j * ldp, W + (long)(j0 + j) * ld + j0, bytes, c.mbar);
+        }
+        mbar_wait(c.mbar, c.mphase);
+        c.mphase ^= 1u;
+        __syncthreads();                                                    // taus
+        return;
+    }
     for (int i = threadIdx.x; i < pw * rows; i += blockDim.x) {
         const int j = i / rows, q = i % rows;
-        P[j * ldp + q] = ld_cg(W + (long)(j0 + j) * Mq + j0 + q);
+        P[j * ldp + q] = ld_cg(W + (long)(j0 + j) * ld + j0 + q);
     }
-    if (with_tau && (int)threadIdx.x < pw) taus[threadIdx.x] = ld_cg(tau + j0 + threadIdx.x);
+    __syncthreads();
 }
 
-// W (Mq x Nq column-major, global) -> R in the upper triangle, reflector tails below, tau[min(Mq, Nq)].
-// Ends with a grid barrier.
-TT_DEV void lin_qr_factor(LinCtx& c, double* W, double* tau, int Mq, int Nq) {
+// trailing column x (global, rows elements from the panel's first row) <- H_{pw-1} ... H_0 x, held in registers
+template <int NQ>
+TT_DEV void lin_trailing_col(double* x, int rows, const double* P, int ldp, const double* taus, int pw, int lane) {
+    double reg[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const int i = lane + 32 * q;
+        reg[q] = i < rows ? ld_cg(x + i) : 0.0;
+    }
+    for (int j = 0; j < pw; ++j)
+        if (taus[j] != 0.0) lin_reflect_reg<NQ>(reg, P + j * ldp, j, rows, taus[j], lane);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const int i = lane + 32 * q;
+        if (i < rows) x[i] = reg[q];
+    }
+}
+
+// W (Mq x Nq column-major, leading dimension ld, global) -> R in the upper triangle, reflector tails below,
+// tau[min(Mq, Nq)].  Ends with a grid barrier.
+TT_DEV void lin_qr_factor(LinCtx& c, double* W, double* tau, int Mq, int Nq, int ld) {
     const int K = imin(Mq, Nq), ldp = c.p.ldp, lane = c.lane, wid = c.wid, nw = c.nw;
-    double* taus = c.smem + c.p.oTaus;
-    double* P = c.panel;
+    const bool psh = c.bulk;                       // panel in shared memory
+    double* taus = lin_smem() + c.p.oTaus;
+    double* scl = taus + TT_QR_PB;                 // 1 / (alpha - beta) of every panel column
+    double* bet = scl + TT_QR_PB;                  // its new diagonal entry
+    double* P = psh ? lin_smem() + c.p.oP : c.panel;
     for (int p0 = 0; p0 < K; p0 += TT_QR_PB) {
         const int pw = imin(TT_QR_PB, K - p0), rows = Mq - p0;
         __syncthreads();
-        lin_load_panel(W, nullptr, Mq, p0, pw, false, P, taus, ldp);
-        __syncthreads();
+        lin_load_panel(c, W, nullptr, ld, Mq, p0, pw, false, P, taus, ldp);
+        // Panel factorisation: every warp derives reflector j from column j redundantly (no broadcast, no serial
+        // section), warp w then updates panel columns j + 1 + w, ...; the tails stay unscaled until the panel is done,
+        // so a column step is one block barrier.
         for (int j = 0; j < pw; ++j) {
-            double* col = P + j * ldp;
-            if (wid == 0) {
-                double s = 0.0;
-                for (int i = j + 1 + lane; i < rows; i += 32) s += col[i] * col[i];
-                s = warp_sum(s);
-                const double alpha = col[j];
-                double tj = 0.0, scale = 0.0, beta = alpha;
-                if (s != 0.0) {
-                    beta = -copysign(sqrt(alpha * alpha + s), alpha);
-                    tj = (beta - alpha) / beta;
-                    scale = 1.0 / (alpha - beta);
-                }
-                __syncwarp();                                  // every lane has read col[j] before lane 0 overwrites it
-                for (int i = j + 1 + lane; i < rows; i += 32) col[i] *= scale;
-                if (lane == 0) {
-                    taus[j] = tj;
-                    col[j] = beta;
-                }
+            const double* col = P + j * ldp;
+            double s = 0.0;
+            for (int i = j + 1 + lane; i < rows; i += 32) s += col[i] * col[i];
+            s = warp_sum(s);
+            const double alpha = col[j];
+            double tj = 0.0, scale = 0.0, beta = alpha;
+            if (s != 0.0) {
+                beta = -copysign(sqrt(alpha * alpha + s), alpha);
+                tj = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
             }
-            __syncthreads();
-            const double tj = taus[j];
             if (tj != 0.0) {
                 for (int cc = j + 1 + wid; cc < pw; cc += nw) {
                     double* x = P + cc * ldp;
-                    double d = lane == 0 ? x[j] : 0.0;
+                    double d = 0.0;
                     for (int i = j + 1 + lane; i < rows; i += 32) d += col[i] * x[i];
-                    d = warp_sum(d) * tj;
+                    d = (warp_sum(d) * scale + x[j]) * tj;
+                    __syncwarp();                              // every lane has read x[j]
                     if (lane == 0) x[j] -= d;
-                    for (int i = j + 1 + lane; i < rows; i += 32) x[i] -= d * col[i];
+                    const double ds = d * scale;
+                    for (int i = j + 1 + lane; i < rows; i += 32) x[i] -= ds * col[i];
                 }
+            }
+            if (wid == nw - 1 && lane == 0) {
+                taus[j] = tj;
+                scl[j] = scale;
+                bet[j] = beta;
             }
             __syncthreads();
         }
+        for (int i = threadIdx.x; i < pw * rows; i += blockDim.x) {
+            const int j = i / rows, q = i % rows;
+            if (q > j) P[j * ldp + q] *= scl[j];
+            else if (q == j) P[j * ldp + j] = bet[j];
+        }
+        __syncthreads();
         if (blockIdx.x == 0) {
             for (int i = threadIdx.x; i < pw * rows; i += blockDim.x) {
                 const int j = i / rows, q = i % rows;
-                W[(long)(p0 + j) * Mq + p0 + q] = P[j * ldp + q];
+                W[(long)(p0 + j) * ld + p0 + q] = P[j * ldp + q];
             }
             if ((int)threadIdx.x < pw) tau[p0 + threadIdx.x] = taus[threadIdx.x];
         }
         for (int cc = p0 + pw + c.gw; cc < Nq; cc += c.GW) {
-            double* x = W + (long)cc * Mq + p0;
-            if (rows <= 32 * TT_LIN_REG) {
-                double reg[TT_LIN_REG];
-#pragma unroll
-                for (int q = 0; q < TT_LIN_REG; ++q) {
-                    const int i = lane + 32 * q;
-                    reg[q] = i < rows ? ld_cg(x + i) : 0.0;
-                }
-                for (int j = 0; j < pw; ++j)
-                    if (taus[j] != 0.0) lin_reflect_reg(reg, P + j * ldp, j, rows, taus[j], lane);
-#pragma unroll
-                for (int q = 0; q < TT_LIN_REG; ++q) {
-                    const int i = lane + 32 * q;
-                    if (i < rows) x[i] = reg[q];
-                }
-            } else {
+            double* x = W + (long)cc * ld + p0;
+            if (rows <= 128) lin_trailing_col<4>(x, rows, P, ldp, taus, pw, lane);
+            else if (rows <= 256) lin_trailing_col<8>(x, rows, P, ldp, taus, pw, lane);
+            else if (rows <= 32 * TT_LIN_REG) lin_trailing_col<TT_LIN_REG>(x, rows, P, ldp, taus, pw, lane);
+            else {
                 for (int j = 0; j < pw; ++j)
                     if (taus[j] != 0.0) lin_reflect_mem(x, 1, P + j * ldp, j, rows, taus[j], lane);
             }
         }
+        fence_proxy_async();                   // columns written here are read by the next panel's bulk copies
         c.sync();
     }
 }
 
 // One vector per warp task t < ntask:  x_t <- H_0 H_1 ... H_{Kq-1} x_t   (= Q x_t, reflectors of a factored W).
 //   init 0: x_t = e_t (only H_j with j <= t act)            -> column t of Q
-//   init 1: x_t = [src[ord[t], 0:Kq] ; 0]                    -> Q [g; 0]
+//   init 1: x_t = [src[ord[t] * src_rs + 0:Kq] ; 0]          -> Q [g; 0]
 // Result element i of task t goes to dst[t * row_stride + i * elem_stride].  W, tau, src must be globally visible.
-TT_DEV void lin_apply_q(LinCtx& c, const double* W, const double* tau, int Mq, int Kq, int ntask, int init,
-                        const double* src, const int* ord, double* dst, long row_stride, long elem_stride) {
+template <int NQ>
+TT_DEV void lin_apply_q_t(LinCtx& c, const double* W, const double* tau, int ld, int Mq, int Kq, int ntask, int init,
+                          const double* src, long src_rs, const int* ord, double* dst, long row_stride, long elem_stride) {
     const int ldp = c.p.ldp, lane = c.lane;
-    double* taus = c.smem + c.p.oTaus;
-    double* P = c.panel;
-    const bool in_regs = Mq <= 32 * TT_LIN_REG;
+    double* taus = lin_smem() + c.p.oTaus;
+    double* P = c.bulk ? lin_smem() + c.p.oP : c.panel;
+    const bool in_regs = NQ > 0;
+    constexpr int NR = NQ > 0 ? NQ : 1;
     for (int base = 0; base < ntask; base += c.GW) {
         const int first = base + blockIdx.x * c.nw;
         if (first >= ntask) break;                              // uniform over the CTA
@@ -227,21 +285,21 @@ TT_DEV void lin_apply_q(LinCtx& c, const double* W, const double* tau, int Mq, i
         const bool active = t < ntask;
         const int tmax = imin(ntask - 1, first + c.nw - 1);
         const int jtop = init == 0 ? imin(tmax, Kq - 1) : Kq - 1;
-        double reg[TT_LIN_REG];
+        double reg[NR];
         double* x = dst + (long)t * row_stride;
         if (active) {
             if (in_regs) {
 #pragma unroll
-                for (int q = 0; q < TT_LIN_REG; ++q) {
+                for (int q = 0; q < NR; ++q) {
                     const int i = lane + 32 * q;
                     if (init == 0) reg[q] = i == t ? 1.0 : 0.0;
-                    else reg[q] = i < Kq ? ld_cg(src + (long)ord[t] * Kq + i) : 0.0;
+                    else reg[q] = i < Kq ? ld_cg(src + (long)ord[t] * src_rs + i) : 0.0;
                 }
             } else {
                 for (int i = lane; i < Mq; i += 32) {
                     double v;
                     if (init == 0) v = i == t ? 1.0 : 0.0;
-                    else v = i < Kq ? ld_cg(src + (long)ord[t] * Kq + i) : 0.0;
+                    else v = i < Kq ? ld_cg(src + (long)ord[t] * src_rs + i) : 0.0;
                     x[(long)i * elem_stride] = v;
                 }
             }
@@ -249,8 +307,7 @@ TT_DEV void lin_apply_q(LinCtx& c, const double* W, const double* tau, int Mq, i
         for (int j0 = (jtop / TT_QR_PB) * TT_QR_PB; j0 >= 0; j0 -= TT_QR_PB) {
             const int pw = imin(TT_QR_PB, Kq - j0);
             __syncthreads();
-            lin_load_panel(W, tau, Mq, j0, pw, true, P, taus, ldp);
-            __syncthreads();
+            lin_load_panel(c, W, tau, ld, Mq, j0, pw, true, P, taus, ldp);
             if (!active) continue;
             for (int jj = pw - 1; jj >= 0; --jj) {
                 const int j = j0 + jj;
@@ -258,18 +315,26 @@ TT_DEV void lin_apply_q(LinCtx& c, const double* W, const double* tau, int Mq, i
                 const double tj = taus[jj];
                 if (tj == 0.0) continue;
                 const double* v = P + jj * ldp - j0;            // v[i] valid for j < i < Mq
-                if (in_regs) lin_reflect_reg(reg, v, j, Mq, tj, lane);
+                if (in_regs) lin_reflect_reg<NR>(reg, v, j, Mq, tj, lane);
                 else lin_reflect_mem(x, elem_stride, v, j, Mq, tj, lane);
             }
         }
         if (active && in_regs) {
 #pragma unroll
-            for (int q = 0; q < TT_LIN_REG; ++q) {
+            for (int q = 0; q < NR; ++q) {
                 const int i = lane + 32 * q;
                 if (i < Mq) x[(long)i * elem_stride] = reg[q];
             }
         }
     }
+}
+TT_DEV void lin_apply_q(LinCtx& c, const double* W, const double* tau, int ld, int Mq, int Kq, int ntask, int init,
+                        const double* src, long src_rs, const int* ord, double* dst, long row_stride, long elem_stride) {
+    if (Mq <= 128) lin_apply_q_t<4>(c, W, tau, ld, Mq, Kq, ntask, init, src, src_rs, ord, dst, row_stride, elem_stride);
+    else if (Mq <= 256) lin_apply_q_t<8>(c, W, tau, ld, Mq, Kq, ntask, init, src, src_rs, ord, dst, row_stride, elem_stride);
+    else if (Mq <= 32 * TT_LIN_REG)
+        lin_apply_q_t<TT_LIN_REG>(c, W, tau, ld, Mq, Kq, ntask, init, src, src_rs, ord, dst, row_stride, elem_stride);
+    else lin_apply_q_t<0>(c, W, tau, ld, Mq, Kq, ntask, init, src, src_rs, ord, dst, row_stride, elem_stride);
 }
 
 // orthogonalise two rows held in shared memory: [row of R (K) | accumulator row (Mj)], total length Ls
@@ -316,11 +381,12 @@ TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, 
     return true;
 }
 
-// (eps * ||G||_F)^2 of the K x K matrix G in global memory, computed redundantly by every CTA
-TT_DEV double lin_noise_floor2(LinCtx& c, const double* G, int K) {
+// (eps * ||G||_F)^2 of the K x K matrix G (row stride ldg, global memory), computed redundantly by every CTA
+TT_DEV double lin_noise_floor2(LinCtx& c, const double* G, int K, int ldg) {
+    if (c.p.floor_factor == 0.0) return 0.0;
     double s = 0.0;
     for (long i = threadIdx.x; i < (long)K * K; i += blockDim.x) {
-        const double v = ld_cg(G + i);
+        const double v = ld_cg(G + (i / K) * ldg + i % K);
         s += v * v;
     }
     __syncthreads();
@@ -329,17 +395,17 @@ TT_DEV double lin_noise_floor2(LinCtx& c, const double* G, int K) {
     return e * e * s;
 }
 
-// block one-sided Jacobi on the rows of G (K x K) with accumulator Jt (K x Mj), both row-major in global memory.
+// block one-sided Jacobi on the K rows [G | Jt | pad] of GJ (row stride ldg, row-major, global memory).
 // Ends with a grid barrier (all rows globally visible).  Returns the number of sweeps.
-TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flags, long long* tm) {
-    const int nb = c.p.nb, Ls = K + Mj, lane = c.lane, wid = c.wid, nw = c.nw;
+TT_DEV int lin_jacobi(LinCtx& c, double* GJ, int K, int Mj, int* flags, long long* tm) {
+    const int nb = c.p.nb, ldg = c.p.ldg, Ls = K + Mj, lane = c.lane, wid = c.wid, nw = c.nw;
     const int nblk = (K + nb - 1) / nb, nbe = nblk + (nblk & 1), npairs = nbe / 2, rounds = nbe - 1;
     const double tol = 2.220446049250313e-16 * sqrt((double)K), tol2 = tol * tol;
     int* rotated = (int*)(c.smem + 36);
-    double* rowsS = c.smem + c.p.oTaus;
+    double* rowsS = lin_smem() + c.p.oRows;
     int sweeps = 0;
     if (K < 2) return 0;
-    const double floor2 = lin_noise_floor2(c, G, K);
+    const double floor2 = lin_noise_floor2(c, GJ, K, ldg);
     for (; sweeps < 60; ++sweeps) {
         for (int t = 0; t < rounds; ++t) {
             for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
@@ -357,18 +423,17 @@ TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flag
                 const int na = imin(nb, K - a * nb), nbb = bvalid ? imin(nb, K - b * nb) : 0;
                 const long long t0 = lin_now();
                 __syncthreads();
-                if (threadIdx.x == 0) *rotated = 0;
-                for (int slot = wid; slot < 2 * nb; slot += nw) {      // slot q < nb -> block a, nb + q -> block b
-                    const int q = slot % nb, blk = slot < nb ? a : b, cnt = slot < nb ? na : nbb;
-                    if (q >= cnt) continue;
-                    const long row = (long)blk * nb + q;
-                    double* dstr = rowsS + (long)slot * Ls;
-#pragma unroll 8
-                    for (int i = lane; i < K; i += 32) dstr[i] = ld_cg(G + row * K + i);
-#pragma unroll 8
-                    for (int i = lane; i < Mj; i += 32) dstr[K + i] = ld_cg(Jt + row * Mj + i);
+                // the rows of a block are contiguous: one bulk copy per block (slot q < nb -> block a, nb + q -> block b)
+                if (threadIdx.x == 0) {
+                    *rotated = 0;
+                    const unsigned ba = (unsigned)(na * ldg) * 8u, bb = (unsigned)(nbb * ldg) * 8u;
+                    fence_proxy_async();
+                    mbar_expect_tx(c.mbar, ba + bb);
+                    bulk_g2s(rowsS, GJ + (long)a * nb * ldg, ba, c.mbar);
+                    if (bb) bulk_g2s(rowsS + (long)nb * ldg, GJ + (long)b * nb * ldg, bb, c.mbar);
                 }
-                __syncthreads();
+                mbar_wait(c.mbar, c.mphase);
+                c.mphase ^= 1u;
                 const long long t1 = lin_now();
                 bool rot = false;
                 if (t == 0 && nb > 1) {
@@ -388,7 +453,7 @@ TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flag
                             }
                             if (x >= cnt || y >= cnt) continue;
                             if (x > y) { const int z = x; x = y; y = z; }
-                            rot |= lin_jacobi_pair(rowsS + (long)(sel * nb + x) * Ls, rowsS + (long)(sel * nb + y) * Ls, K, Ls,
+                            rot |= lin_jacobi_pair(rowsS + (long)(sel * nb + x) * ldg, rowsS + (long)(sel * nb + y) * ldg, K, Ls,
                                                    tol2, floor2, lane);
                         }
                         __syncthreads();
@@ -399,7 +464,7 @@ TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flag
                         for (int i = wid; i < nb; i += nw) {
                             const int jb = (i + u) % nb;
                             if (i >= na || jb >= nbb) continue;
-                            rot |= lin_jacobi_pair(rowsS + (long)i * Ls, rowsS + (long)(nb + jb) * Ls, K, Ls, tol2, floor2, lane);
+                            rot |= lin_jacobi_pair(rowsS + (long)i * ldg, rowsS + (long)(nb + jb) * ldg, K, Ls, tol2, floor2, lane);
                         }
                         __syncthreads();
                     }
@@ -408,14 +473,10 @@ TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flag
                 __syncthreads();
                 const long long t2 = lin_now();
                 if (*rotated) {
-                    for (int slot = wid; slot < 2 * nb; slot += nw) {
-                        const int q = slot % nb, blk = slot < nb ? a : b, cnt = slot < nb ? na : nbb;
-                        if (q >= cnt) continue;
-                        const long row = (long)blk * nb + q;
-                        const double* srcr = rowsS + (long)slot * Ls;
-                        for (int i = lane; i < K; i += 32) G[row * K + i] = srcr[i];
-                        for (int i = lane; i < Mj; i += 32) Jt[row * Mj + i] = srcr[K + i];
-                    }
+                    double* ga = GJ + (long)a * nb * ldg;
+                    double* gb = GJ + (long)b * nb * ldg;
+                    for (int i = threadIdx.x; i < na * ldg; i += blockDim.x) ga[i] = rowsS[i];
+                    for (int i = threadIdx.x; i < nbb * ldg; i += blockDim.x) gb[i] = rowsS[(long)nb * ldg + i];
                     if (threadIdx.x == 0) flags[sweeps] = 1;
                 }
                 tm[0] += t1 - t0;
@@ -423,6 +484,7 @@ TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flag
                 tm[2] += lin_now() - t2;
             }
             const long long t3 = lin_now();
+            fence_proxy_async();               // rows written through the generic proxy are read by bulk copies next round
             c.sync();
             tm[3] += lin_now() - t3;
         }
@@ -434,23 +496,25 @@ TT_DEV int lin_jacobi(LinCtx& c, double* G, double* Jt, int K, int Mj, int* flag
     return sweeps;
 }
 
-// Single-CTA variant for unfoldings whose rows [R | accumulator] fit in shared memory (K * (K + Mj) doubles): every
+// Single-CTA variant for unfoldings whose rows [R | accumulator] fit in shared memory (K * ldg doubles): every
 // row stays resident for the whole iteration, each warp owns one row pair of a round-robin step, and a step costs one
-// block barrier.  G, Jt are read once and written once.
-TT_DEV int lin_jacobi_resident(LinCtx& c, double* G, double* Jt, int K, int Mj) {
-    const int Ls = K + Mj, lane = c.lane, wid = c.wid, nw = c.nw;
+// block barrier.  The rows are read once (one bulk copy) and written once.
+TT_DEV int lin_jacobi_resident(LinCtx& c, double* GJ, int K, int Mj) {
+    const int ldg = c.p.ldg, Ls = K + Mj, lane = c.lane, wid = c.wid, nw = c.nw;
     const int Ke = K + (K & 1), half = Ke / 2;
     const double tol = 2.220446049250313e-16 * sqrt((double)K), tol2 = tol * tol;
     int* rotated = (int*)(c.smem + 36);
-    double* rowsS = c.smem + c.p.oTaus;
+    double* rowsS = lin_smem() + c.p.oRows;
     if (K < 2) return 0;
-    const double floor2 = lin_noise_floor2(c, G, K);
+    const double floor2 = lin_noise_floor2(c, GJ, K, ldg);
     __syncthreads();
-    for (int row = wid; row < K; row += nw) {
-        double* dstr = rowsS + (long)row * Ls;
-        for (int i = lane; i < K; i += 32) dstr[i] = ld_cg(G + (long)row * K + i);
-        for (int i = lane; i < Mj; i += 32) dstr[K + i] = ld_cg(Jt + (long)row * Mj + i);
+    if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(c.mbar, (unsigned)(K * ldg) * 8u);
+        bulk_g2s(rowsS, GJ, (unsigned)(K * ldg) * 8u, c.mbar);
     }
+    mbar_wait(c.mbar, c.mphase);
+    c.mphase ^= 1u;
     int sweeps = 0;
     for (; sweeps < 60;) {
         __syncthreads();
@@ -469,7 +533,7 @@ TT_DEV int lin_jacobi_resident(LinCtx& c, double* G, double* Jt, int K, int Mj) 
                 }
                 if (x >= K || y >= K) continue;
                 if (x > y) { const int z = x; x = y; y = z; }
-                rot |= lin_jacobi_pair(rowsS + (long)x * Ls, rowsS + (long)y * Ls, K, Ls, tol2, floor2, lane);
+                rot |= lin_jacobi_pair(rowsS + (long)x * ldg, rowsS + (long)y * ldg, K, Ls, tol2, floor2, lane);
             }
             __syncthreads();
         }
@@ -478,11 +542,7 @@ TT_DEV int lin_jacobi_resident(LinCtx& c, double* G, double* Jt, int K, int Mj) 
         ++sweeps;
         if (*rotated == 0) break;
     }
-    for (int row = wid; row < K; row += nw) {
-        const double* srcr = rowsS + (long)row * Ls;
-        for (int i = lane; i < K; i += 32) G[(long)row * K + i] = srcr[i];
-        for (int i = lane; i < Mj; i += 32) Jt[(long)row * Mj + i] = srcr[K + i];
-    }
+    for (int i = threadIdx.x; i < K * ldg; i += blockDim.x) GJ[i] = rowsS[i];
     c.sync();
     return sweeps;
 }
@@ -498,52 +558,59 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
     double* ws = p.ws + (long)p.nbatch * 40 + (long)batch * p.ws_per;
     if (p.oPg >= 0) c.panel = ws + p.oPg;
     const double* A = p.A + (long)batch * p.a_bs;
-    const int M = p.M, N = p.N, K = imin(M, N), M1 = p.M1, Mj = p.Mj;
+    const int M = p.M, N = p.N, K = imin(M, N), M1 = p.M1, Mj = p.Mj, ld1 = p.ld1, ldk = p.ldk, ldg = p.ldg;
     const bool wide = p.mode == 0 && M < N;
     double* W1 = ws + p.oW1;
     double* tau1 = ws + p.oTau1;
     double* W2 = ws + p.oW2;
     double* tau2 = ws + p.oTau2;
-    double* G = ws + p.oG;
-    double* Jt = ws + p.oJt;
+    double* G = ws + p.oG;            // rows [G (K) | Jt (Mj) | pad], stride ldg
+    double* Jt = G + K;
     double* sv = ws + p.oSv;
     double* U = p.U + (long)batch * M * K;
     double* Wt = p.Wt + (long)batch * K * N;
     const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gth = (long)gridDim.x * blockDim.x;
     const long long t_start = lin_now();
     long long tm[4] = {0, 0, 0, 0};
+    if (threadIdx.x == 0) mbar_init(c.mbar, 1);
+    __syncthreads();
 
     // working copy, column-major: A (M x N), or A^T (N x M) for a wide SVD
     for (long i = gtid; i < (long)M * N; i += gth) {
         const long row = i / N, col = i % N;
         const double v = A[row * p.a_rs + col * p.a_cs];
-        if (!wide) W1[row + col * M] = v;
-        else W1[col + row * N] = v;
+        if (!wide) W1[row + col * ld1] = v;
+        else W1[col + row * ld1] = v;
     }
+    fence_proxy_async();
     c.sync();
-    lin_qr_factor(c, W1, tau1, M1, p.N1);
+    lin_qr_factor(c, W1, tau1, M1, p.N1, ld1);
     if (p.mode == 1) {
         for (long i = gtid; i < (long)K * N; i += gth) {
             const long row = i / N, col = i % N;
-            Wt[i] = row <= col ? ld_cg(W1 + row + col * M) : 0.0;
+            Wt[i] = row <= col ? ld_cg(W1 + row + col * ld1) : 0.0;
         }
-        lin_apply_q(c, W1, tau1, M, K, K, 0, nullptr, nullptr, U, 1, K);      // column t of Q -> Q (M x K) row-major
+        fence_proxy_async();
+        c.sync();                                   // the factored panels written by CTA 0 are read by bulk copies
+        lin_apply_q(c, W1, tau1, ld1, M, K, K, 0, nullptr, 0, nullptr, U, 1, K);   // column t of Q -> Q (M x K) row-major
         return;
     }
     const double* Wq = W1;      // factor whose R is rotated and whose Q^T seeds the accumulator
     const double* tq = tau1;
-    int Mq = M1;
+    int Mq = M1, ldq = ld1;
     if (wide || p.triple) {
         // L = R1^T (K x K lower triangular), column-major working copy, second QR
         for (long i = gtid; i < (long)K * K; i += gth) {
             const long row = i % K, col = i / K;
-            W2[i] = col <= row ? ld_cg(W1 + col + row * M1) : 0.0;
+            W2[row + col * ldk] = col <= row ? ld_cg(W1 + col + row * ld1) : 0.0;
         }
+        fence_proxy_async();
         c.sync();
-        lin_qr_factor(c, W2, tau2, K, K);
+        lin_qr_factor(c, W2, tau2, K, K, ldk);
         Wq = W2;
         tq = tau2;
         Mq = K;
+        ldq = ldk;
     }
     if (p.triple) {
         // tall: a third factorisation R2^T = Q3 R3 puts the accumulator back on the U side:
@@ -552,29 +619,36 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
         double* tau3 = ws + p.oTau3;
         for (long i = gtid; i < (long)K * K; i += gth) {
             const long row = i % K, col = i / K;
-            W3[i] = col <= row ? ld_cg(W2 + col + row * K) : 0.0;
+            W3[row + col * ldk] = col <= row ? ld_cg(W2 + col + row * ldk) : 0.0;
         }
+        fence_proxy_async();
         c.sync();
-        lin_qr_factor(c, W3, tau3, K, K);
+        lin_qr_factor(c, W3, tau3, K, K, ldk);
         Wq = W3;
         tq = tau3;
         Mq = K;
+        ldq = ldk;
     }
     const long long t_qr = lin_now();
     for (long i = gtid; i < (long)K * K; i += gth) {
         const long row = i / K, col = i % K;
-        G[i] = row <= col ? ld_cg(Wq + row + col * Mq) : 0.0;
+        G[row * ldg + col] = row <= col ? ld_cg(Wq + row + col * ldq) : 0.0;
     }
-    lin_apply_q(c, Wq, tq, Mq, K, K, 0, nullptr, nullptr, Jt, Mj, 1);          // rows of Q^T (K x Mq), Mj == Mq
+    for (long i = gtid; i < (long)K * (ldg - K - Mj); i += gth)      // pad columns travel with the bulk copies
+        G[(i / (ldg - K - Mj)) * ldg + K + Mj + i % (ldg - K - Mj)] = 0.0;
+    fence_proxy_async();
+    c.sync();
+    lin_apply_q(c, Wq, tq, ldq, Mq, K, K, 0, nullptr, 0, nullptr, Jt, ldg, 1);      // rows of Q^T (K x Mq), Mj == Mq
+    fence_proxy_async();
     c.sync();
     const long long t_q = lin_now();
-    const int sweeps = p.resident ? lin_jacobi_resident(c, G, Jt, K, Mj) : lin_jacobi(c, G, Jt, K, Mj, flags, tm);
+    const int sweeps = p.resident ? lin_jacobi_resident(c, G, K, Mj) : lin_jacobi(c, G, K, Mj, flags, tm);
     const long long t_jac = lin_now();
     // singular values = row norms
     for (int i = c.gw; i < K; i += c.GW) {
         double s = 0.0;
         for (int q = c.lane; q < K; q += 32) {
-            const double g = ld_cg(G + (long)i * K + q);
+            const double g = ld_cg(G + (long)i * ldg + q);
             s += g * g;
         }
         s = warp_sum(s);
@@ -596,14 +670,14 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
     double* S = p.S + (long)batch * K;
     for (long i = gtid; i < K; i += gth) S[i] = svS[ord[i]];
     if (p.triple) {
-        lin_apply_q(c, W1, tau1, M1, K, K, 1, Jt, ord, U, 1, K);               // U columns = Q1 [(Q3 J) column; 0]
-        lin_apply_q(c, W2, tau2, K, K, K, 1, G, ord, Wt, N, 1);                // W rows = Q2 g  (N == K)
+        lin_apply_q(c, W1, tau1, ld1, M1, K, K, 1, Jt, ldg, ord, U, 1, K);          // U columns = Q1 [(Q3 J) column; 0]
+        lin_apply_q(c, W2, tau2, ldk, K, K, K, 1, G, ldg, ord, Wt, N, 1);           // W rows = Q2 g  (N == K)
     } else if (!wide) {
-        for (long i = gtid; i < (long)M * K; i += gth) U[i] = ld_cg(Jt + (long)ord[i % K] * Mj + i / K);
-        for (long i = gtid; i < (long)K * N; i += gth) Wt[i] = ld_cg(G + (long)ord[i / N] * K + i % N);
+        for (long i = gtid; i < (long)M * K; i += gth) U[i] = ld_cg(Jt + (long)ord[i % K] * ldg + i / K);
+        for (long i = gtid; i < (long)K * N; i += gth) Wt[i] = ld_cg(G + (long)ord[i / N] * ldg + i % N);
     } else {
-        for (long i = gtid; i < (long)M * K; i += gth) U[i] = ld_cg(Jt + (long)ord[i % K] * Mj + i / K);
-        lin_apply_q(c, W1, tau1, M1, K, K, 1, G, ord, Wt, N, 1);               // W rows = Q1 [g; 0]
+        for (long i = gtid; i < (long)M * K; i += gth) U[i] = ld_cg(Jt + (long)ord[i % K] * ldg + i / K);
+        lin_apply_q(c, W1, tau1, ld1, M1, K, K, 1, G, ldg, ord, Wt, N, 1);          // W rows = Q1 [g; 0]
     }
     if (gtid == 0 && p.info) {
         // [0] sweeps; ns: [1] QR(s), [2] Q^T set-up, [3] Jacobi, [4] grid, [5] block rows,
@@ -620,6 +694,7 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
         info[8] = (int)tm[2];
         info[9] = (int)tm[3];
         info[10] = (int)(lin_now() - t_start);
+        info[11] = p.cluster;
     }
 }
 
@@ -628,6 +703,7 @@ static int g_resident_max_dim = 32;
 static double g_floor_factor = 0.0;
 static int g_tall_triple_qr = 1;
 static int g_coop_threads = 256;
+static int g_use_cluster = 1;
 
 struct LinPlan {
     LinParams p;
@@ -636,6 +712,8 @@ struct LinPlan {
     long smem_bytes;
     long ws_total;
 };
+
+static long even_up(long v) { return v + (v & 1); }
 
 // shapes, workspace carve-up, shared-memory layout and grid of one call; returns 0 or an error code
 static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
@@ -648,16 +726,21 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
     p.N1 = wide ? M : N;
     p.triple = (mode == 0 && !wide && g_tall_triple_qr) ? 1 : 0;
     p.Mj = (wide || p.triple) ? (int)K : M;
+    p.ld1 = (int)even_up(p.M1);
+    p.ldk = (int)even_up(K);
+    p.ldg = (int)even_up(K + p.Mj);
+    p.cluster = 0;
+    // every array starts at an even offset (16-byte aligned: bulk copies)
     long o = 0;
-    p.oW1 = o; o += (long)M * N;
-    p.oTau1 = o; o += K;
-    p.oW2 = o; o += (wide || p.triple) ? K * K : 0;
-    p.oTau2 = o; o += (wide || p.triple) ? K : 0;
-    p.oW3 = o; o += p.triple ? K * K : 0;
-    p.oTau3 = o; o += p.triple ? K : 0;
-    p.oG = o; o += mode == 0 ? K * K : 0;
-    p.oJt = o; o += mode == 0 ? K * p.Mj : 0;
-    p.oSv = o; o += K;
+    p.oW1 = o; o += (long)p.ld1 * p.N1;
+    p.oTau1 = o; o += even_up(K);
+    p.oW2 = o; o += (wide || p.triple) ? (long)p.ldk * K : 0;
+    p.oTau2 = o; o += (wide || p.triple) ? even_up(K) : 0;
+    p.oW3 = o; o += p.triple ? (long)p.ldk * K : 0;
+    p.oTau3 = o; o += p.triple ? even_up(K) : 0;
+    p.oG = o; o += mode == 0 ? K * p.ldg : 0;
+    p.oJt = p.oG + K;
+    p.oSv = o; o += even_up(K);
     DevInfo di = dev_info();
     // 256-thread CTAs (8 warps = the 8 concurrent row pairs of a block-pair step; measured on B200: the pairwise
     // rotations are bound by shared-memory bandwidth, 16 warps per CTA do not finish a step sooner); the resident
@@ -667,38 +750,43 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
 #else
     pl.threads = g_coop_threads;
 #endif
-    const int nw = pl.threads / 32;
     p.ldp = p.M1 + (p.M1 & 1);
-    // a panel of TT_QR_PB columns of M1 rows normally sits in shared memory; columns too long for that keep the
-    // panel in the workspace and the matrix is factored by one CTA (rare: unfoldings with > ~3000 rows)
-    const bool panel_global = (40L + (K + 1) / 2 + 1 + K + TT_QR_PB + (long)TT_QR_PB * p.ldp) * 8 > di.smem_optin - 1024;
-    p.oPg = -1;
-    if (panel_global) { p.oPg = o; o += (long)TT_QR_PB * p.ldp; }
-    p.ws_per = o + (o & 1);
-    pl.ws_total = (long)nbatch * 40 + (long)nbatch * p.ws_per;
     p.oOrd = 40;
     p.oSvS = p.oOrd + (int)(K + 1) / 2 + 1;
-    p.oTaus = p.oSvS + (int)K;
-    p.oP = p.oTaus + TT_QR_PB;
-    const long Ls = K + p.Mj;
+    p.oTaus = (int)even_up(p.oSvS + (int)K);
+    p.oP = p.oTaus + 3 * TT_QR_PB;                  // tau, 1 / (alpha - beta), beta of the panel columns
+    p.oRows = p.oTaus;
+    // a panel of TT_QR_PB columns of M1 rows normally sits in shared memory; columns too long for that keep the
+    // panel in the workspace and the matrix is factored by one CTA (rare: unfoldings with > ~3000 rows)
+    const bool panel_global = ((long)p.oP + (long)TT_QR_PB * p.ldp) * 8 > di.smem_optin - 1024;
+    p.oPg = -1;
+    if (panel_global) { p.oPg = o; o += (long)TT_QR_PB * p.ldp; }
+    p.ws_per = even_up(o);
+    pl.ws_total = (long)nbatch * 40 + (long)nbatch * p.ws_per;
+    const long ldg = p.ldg;
     const long qr_doubles = p.oP + (panel_global ? 0 : (long)TT_QR_PB * p.ldp);
+    // Jacobi block rows: 8, raised (even) until the block pairs of a round fit one thread-block cluster of 16 CTAs,
+    // lowered until two blocks fit the shared memory of a CTA
     int nb = 8;
-    while (nb > 1 && (p.oTaus + 2L * nb * Ls) * 8 > di.smem_optin - 1024) nb /= 2;
+    while ((K + nb - 1) / nb > 32 && (p.oRows + 2L * (nb + 2) * ldg) * 8 <= di.smem_optin - 1024) nb += 2;
+    while (nb > 1 && (p.oRows + 2L * nb * ldg) * 8 > di.smem_optin - 1024) nb /= 2;
     p.nb = nb;
-    long jac_doubles = mode == 0 ? p.oTaus + 2L * nb * Ls : 0;
+    long jac_doubles = mode == 0 ? p.oRows + 2L * nb * ldg : 0;
     // every row resident in one CTA's shared memory when it fits (forced multi-CTA runs of the tests excepted)
     // (measured on B200: one SM's issue slots bound the resident variant, so beyond K ~ 32 a single matrix is faster
     // spread over several CTAs; batched calls keep one CTA per matrix)
-    p.resident = (mode == 0 && K >= 2 && (p.oTaus + K * Ls) * 8 <= di.smem_optin - 1024 &&
+    p.resident = (mode == 0 && K >= 2 && (p.oRows + K * ldg) * 8 <= di.smem_optin - 1024 &&
                   (nbatch > 1 || K <= g_resident_max_dim) && !(nbatch == 1 && g_coop_min_dim <= 1)) ? 1 : 0;
-    if (p.resident) jac_doubles = p.oTaus + K * Ls;
+    if (p.resident) jac_doubles = p.oRows + K * ldg;
     pl.smem_bytes = 8 * (qr_doubles > jac_doubles ? qr_doubles : jac_doubles);
     if (pl.smem_bytes > di.smem_optin)
         return fail(4, "linalg: %d x %d does not fit the kernel's shared memory (%ld B)", M, N, pl.smem_bytes);
     int G = 1;
     if (nbatch == 1 && K >= g_coop_min_dim && K >= 2 && !panel_global && !p.resident) {
         const int nblk = (int)((K + nb - 1) / nb), npairs = (nblk + 1) / 2;
-        G = imax(npairs, (int)((K + 7) / 8));          // Jacobi keeps npairs CTAs busy, the QR phases one warp per column
+        if (mode == 0) G = npairs;                      // Jacobi keeps npairs CTAs busy
+        else G = (int)((K + 7) / 8);                    // the QR phases: one warp per trailing column
+        G = imin(G, 16);                                // one thread-block cluster
         if (g_coop_min_dim <= 1) G = imax(G, 2);        // forced (tests): always exercise the multi-CTA path
         G = imax(1, imin(G, imin(64, di.sms)));
     }
@@ -719,16 +807,18 @@ static int lin_launch(int mode, const double* A, long a_rs, long a_cs, long a_bs
     LinParams& p = pl.p;
     p.A = A; p.a_rs = a_rs; p.a_cs = a_cs; p.a_bs = a_bs;
     p.U = U; p.S = S; p.Wt = Wt; p.info = info; p.ws = ws;
+    if (((uintptr_t)ws & 15) != 0) return fail(1, "linalg: workspace must be 16-byte aligned");
     if (dev_memset(ws, 0, (size_t)nbatch * 40 * 8, st)) return fail(5, "linalg: memset failed");
     int G = pl.grid;
+    if (G > 1 && g_use_cluster &&
+        cluster_launch_possible(k_linalg<512>, G, nbatch, dim3(pl.threads), (size_t)pl.smem_bytes)) {
+        p.cluster = 1;
+        return launch_kernel_cluster("k_linalg", k_linalg<512>, dim3(G, nbatch), dim3(pl.threads), (size_t)pl.smem_bytes, st, p);
+    }
 #ifndef TTIPM_EMU
     if (G > 1) {
         DevInfo di = dev_info();
-        static int optin_done = 0;
-        if (!optin_done) {
-            cudaFuncSetAttribute((const void*)k_linalg<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
-            optin_done = 1;
-        }
+        cudaFuncSetAttribute((const void*)k_linalg<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linalg<512>, pl.threads, (size_t)pl.smem_bytes);
         if (per_sm < 1) return fail(4, "linalg: kernel does not fit on an SM with %ld B shared memory", pl.smem_bytes);
@@ -747,6 +837,12 @@ using namespace ttipm;
 extern "C" int ttipm_linalg_coop_min_dim(int min_dim) {
     const int old = g_coop_min_dim;
     if (min_dim > 0) g_coop_min_dim = min_dim;
+    return old;
+}
+
+extern "C" int ttipm_linalg_use_cluster(int on) {
+    const int old = g_use_cluster;
+    if (on >= 0) g_use_cluster = on ? 1 : 0;
     return old;
 }
 

@@ -81,6 +81,7 @@ SIGNATURES = {
     "ttipm_linalg_noise_floor": (C.c_double, [C.c_double]),
     "ttipm_linalg_tall_triple_qr": (C.c_int, [C.c_int]),
     "ttipm_linalg_threads": (C.c_int, [C.c_int]),
+    "ttipm_linalg_use_cluster": (C.c_int, [C.c_int]),
     "ttipm_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, i64, i64, i64, C.c_void_p, i64, i64,
                              i64, C.c_double, C.c_void_p, i64, i64, i64, C.c_int, C.c_void_p]),
 }
