@@ -80,11 +80,13 @@ struct LinCtx {
     unsigned long long* mbar;    // byte-counting barrier of the bulk copies (shared memory)
     unsigned mphase;
     bool bulk;           // panel in shared memory: bulk copies apply
+    long long tq[4];     // QR phase timers of this CTA (ns): panel load, panel factorisation, trailing update, barrier
     TT_DEVM LinCtx(const LinParams& pp, double* s, unsigned* bar) : p(pp), smem(s), barrier(bar), epoch(0) {
         panel = s + pp.oP;
         mbar = (unsigned long long*)(s + 38);
         mphase = 0;
         bulk = pp.oPg < 0;
+        tq[0] = tq[1] = tq[2] = tq[3] = 0;
         lane = threadIdx.x & 31;
         wid = threadIdx.x >> 5;
         nw = blockDim.x >> 5;
@@ -116,22 +118,40 @@ TT_DEV long long lin_now() { return 0; }
 TT_DEV double lin_rsqrt(double x) { return 1.0 / sqrt(x); }
 #endif
 
+// Jacobi rotation that orthogonalises two rows with squared norms saa, sbb and inner product sab != 0:
+//   a' = cs a - sn b,  b' = sn a + cs b,  |theta| <= pi / 4.
+// With d = sbb - saa and h = sqrt(d^2 + 4 sab^2):  cos 2theta = |d| / h,  sin 2theta = sign(d) 2 sab / h, so
+//   cs^2 = (1 + |d| / h) / 2,  sn = sign(d) sab / (h cs)
+// -- two reciprocal square roots in sequence instead of sqrt, division and reciprocal square root (the pair step of the
+// block Jacobi iteration is a dependent chain; this shortens its scalar part).
+TT_DEV void lin_rotation(double saa, double sbb, double sab, double& cs, double& sn) {
+    const double d = sbb - saa;
+    const double rh = lin_rsqrt(d * d + 4.0 * sab * sab);
+    const double c2 = 0.5 + 0.5 * fabs(d) * rh;
+    const double rc = lin_rsqrt(c2);
+    cs = c2 * rc;
+    sn = copysign(sab * rh * rc, d * sab);
+}
+
 // x <- (I - tj v v^T) x for a vector held in registers with the fixed mapping element i <-> (lane, q = i / 32);
 // v[j] = 1 implicit, v[i] given for j < i < len (v may point before its first valid element), zero above j.
 // NQ = register chunks actually in use (32 * NQ >= len).
 template <int NQ>
 TT_DEV void lin_reflect_reg(double (&reg)[NQ], const double* v, int j, int len, double tj, int lane) {
-    double d = 0.0;
-    double vv[NQ];
+    double d2[2] = {0.0, 0.0};
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         const int i = lane + 32 * q;
-        vv[q] = (i > j && i < len) ? v[i] : (i == j ? 1.0 : 0.0);
-        d += vv[q] * reg[q];
+        const double vv = (i > j && i < len) ? v[i] : (i == j ? 1.0 : 0.0);
+        d2[q & 1] += vv * reg[q];
     }
-    d = warp_sum(d) * tj;
+    const double d = warp_sum(d2[0] + d2[1]) * tj;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) reg[q] -= d * vv[q];
+    for (int q = 0; q < NQ; ++q) {
+        const int i = lane + 32 * q;
+        const double vv = (i > j && i < len) ? v[i] : (i == j ? 1.0 : 0.0);
+        reg[q] -= d * vv;
+    }
 }
 // same for a vector in memory (len > 32 * TT_LIN_REG); element i at x[i * xs]; a thread only re-reads its own writes
 TT_DEV void lin_reflect_mem(double* x, long xs, const double* v, int j, int len, double tj, int lane) {
@@ -203,27 +223,43 @@ TT_DEV void lin_qr_factor(LinCtx& c, double* W, double* tau, int Mq, int Nq, int
     for (int p0 = 0; p0 < K; p0 += TT_QR_PB) {
         const int pw = imin(TT_QR_PB, K - p0), rows = Mq - p0;
         __syncthreads();
+        const long long tq0 = lin_now();
         lin_load_panel(c, W, nullptr, ld, Mq, p0, pw, false, P, taus, ldp);
+        const long long tq1 = lin_now();
         // Panel factorisation: every warp derives reflector j from column j redundantly (no broadcast, no serial
         // section), warp w then updates panel columns j + 1 + w, ...; the tails stay unscaled until the panel is done,
         // so a column step is one block barrier.
         for (int j = 0; j < pw; ++j) {
             const double* col = P + j * ldp;
-            double s = 0.0;
-            for (int i = j + 1 + lane; i < rows; i += 32) s += col[i] * col[i];
-            s = warp_sum(s);
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+            int i = j + 1 + lane;
+            for (; i + 96 < rows; i += 128) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) s4[u] += col[i + 32 * u] * col[i + 32 * u];
+            }
+            for (int u = 0; i < rows; i += 32, ++u) s4[u] += col[i] * col[i];
+            const double s = warp_sum((s4[0] + s4[1]) + (s4[2] + s4[3]));
             const double alpha = col[j];
             double tj = 0.0, scale = 0.0, beta = alpha;
             if (s != 0.0) {
-                beta = -copysign(sqrt(alpha * alpha + s), alpha);
-                tj = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
+                // beta = -sign(alpha) * nrm, tau = (beta - alpha) / beta, scale = 1 / (alpha - beta) with one reciprocal
+                // square root and one division:  1 / beta = -sign(alpha) * rn,  alpha - beta = sign(alpha) (|alpha| + nrm)
+                const double q2 = alpha * alpha + s, rn = lin_rsqrt(q2), nrm = q2 * rn, an = fabs(alpha) + nrm;
+                beta = -copysign(nrm, alpha);
+                tj = an * rn;
+                scale = copysign(1.0 / an, alpha);
             }
             if (tj != 0.0) {
                 for (int cc = j + 1 + wid; cc < pw; cc += nw) {
                     double* x = P + cc * ldp;
-                    double d = 0.0;
-                    for (int i = j + 1 + lane; i < rows; i += 32) d += col[i] * x[i];
+                    double d4[4] = {0.0, 0.0, 0.0, 0.0};
+                    int i2 = j + 1 + lane;
+                    for (; i2 + 96 < rows; i2 += 128) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) d4[u] += col[i2 + 32 * u] * x[i2 + 32 * u];
+                    }
+                    for (int u = 0; i2 < rows; i2 += 32, ++u) d4[u] += col[i2] * x[i2];
+                    double d = (d4[0] + d4[1]) + (d4[2] + d4[3]);
                     d = (warp_sum(d) * scale + x[j]) * tj;
                     __syncwarp();                              // every lane has read x[j]
                     if (lane == 0) x[j] -= d;
@@ -251,6 +287,7 @@ TT_DEV void lin_qr_factor(LinCtx& c, double* W, double* tau, int Mq, int Nq, int
             }
             if ((int)threadIdx.x < pw) tau[p0 + threadIdx.x] = taus[threadIdx.x];
         }
+        const long long tq2 = lin_now();
         for (int cc = p0 + pw + c.gw; cc < Nq; cc += c.GW) {
             double* x = W + (long)cc * ld + p0;
             if (rows <= 128) lin_trailing_col<4>(x, rows, P, ldp, taus, pw, lane);
@@ -261,8 +298,13 @@ TT_DEV void lin_qr_factor(LinCtx& c, double* W, double* tau, int Mq, int Nq, int
                     if (taus[j] != 0.0) lin_reflect_mem(x, 1, P + j * ldp, j, rows, taus[j], lane);
             }
         }
+        const long long tq3 = lin_now();
         fence_proxy_async();                   // columns written here are read by the next panel's bulk copies
         c.sync();
+        c.tq[0] += tq1 - tq0;
+        c.tq[1] += tq2 - tq1;
+        c.tq[2] += tq3 - tq2;
+        c.tq[3] += lin_now() - tq3;
     }
 }
 
@@ -346,14 +388,26 @@ TT_DEV void lin_apply_q(LinCtx& c, const double* W, const double* tau, int ld, i
 // U * W = A holds regardless (only rotations are applied); singular values above the floor are unaffected, the ones
 // below it carry an absolute error of eps * sigma_max like LAPACK's.
 TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, double floor2, int lane) {
-    double saa = 0.0, sbb = 0.0, sab = 0.0;
-#pragma unroll 4
-    for (int i = lane; i < K; i += 32) {
-        const double x = ra[i], y = rb[i];
+    double saa = 0.0, sbb = 0.0, sab = 0.0, taa = 0.0, tbb = 0.0, tab = 0.0;
+    int i0 = lane;
+    for (; i0 + 32 < K; i0 += 64) {
+        const double x = ra[i0], y = rb[i0], x2 = ra[i0 + 32], y2 = rb[i0 + 32];
+        saa += x * x;
+        sbb += y * y;
+        sab += x * y;
+        taa += x2 * x2;
+        tbb += y2 * y2;
+        tab += x2 * y2;
+    }
+    if (i0 < K) {
+        const double x = ra[i0], y = rb[i0];
         saa += x * x;
         sbb += y * y;
         sab += x * y;
     }
+    saa += taa;
+    sbb += tbb;
+    sab += tab;
 #ifndef TTIPM_EMU
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {           // three interleaved butterflies
@@ -368,9 +422,8 @@ TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, 
 #endif
     if (!(sab * sab > tol2 * saa * sbb) || fmin(saa, sbb) <= floor2) return false;
     // tan of the rotation angle: zeta = (sbb - saa) / (2 sab), tg = sign(zeta) / (|zeta| + sqrt(1 + zeta^2))
-    const double d = sbb - saa;
-    const double tg = 2.0 * sab / (d + copysign(sqrt(d * d + 4.0 * sab * sab), d));
-    const double cs = lin_rsqrt(1.0 + tg * tg), sn = cs * tg;
+    double cs, sn;
+    lin_rotation(saa, sbb, sab, cs, sn);
     const double c1 = cs, s1 = -sn, c2 = sn, s2 = cs;
 #pragma unroll 4
     for (int i = lane; i < Ls; i += 32) {
@@ -379,6 +432,91 @@ TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, 
         rb[i] = c2 * x + s2 * y;
     }
     return true;
+}
+
+// Cross pairs of two row blocks held in shared memory (block a: slots 0..nb-1, block b: slots nb..2nb-1).  Warp i
+// keeps row i of block a in REGISTERS for all nb steps of the round and meets row (i + u) % nb of block b at step u, so
+// the shared-memory traffic of a step is one read and one write of the b row (the smem-only form moves 2.5x as much
+// and was bound by shared-memory bandwidth).  NQ = register chunks per row (32 * NQ >= Ls).
+template <int NQ, bool RB_REGS>
+TT_DEV bool lin_cross_pairs_reg(double* rowsS, int nb, int na, int nbb, int K, int Ls, int ldg, double tol2, double floor2,
+                                int lane, int wid, int nw) {
+    bool rot = false;
+    for (int i0 = 0; i0 < nb; i0 += nw) {                 // one pass when the CTA has at least nb warps
+        const int i = i0 + wid;
+        const bool have = i < na;
+        double ra[NQ];
+        if (have) {
+            const double* rap = rowsS + (long)i * ldg;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int e = lane + 32 * q;
+                ra[q] = e < Ls ? rap[e] : 0.0;
+            }
+        }
+        for (int u = 0; u < nb; ++u) {
+            const int jb = (i + u) % nb;
+            if (have && jb < nbb) {
+                double* rbp = rowsS + (long)(nb + jb) * ldg;
+                double rb[RB_REGS ? NQ : 1];                  // long rows: the b row is re-read for the rotation
+                // fp64 FMA latency on B200 is ~23 cycles (tools/lat_bench.cu): split every sum over independent
+                // accumulators so the dot products are not one dependent chain
+                double paa[2] = {0.0, 0.0}, pbb[2] = {0.0, 0.0}, pab[2] = {0.0, 0.0};
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const int e = lane + 32 * q;
+                    if (RB_REGS) {
+                        rb[q] = e < Ls ? rbp[e] : 0.0;
+                        if (e < K) {
+                            paa[q & 1] += ra[q] * ra[q];
+                            pbb[q & 1] += rb[q] * rb[q];
+                            pab[q & 1] += ra[q] * rb[q];
+                        }
+                    } else if (e < K) {
+                        const double y = rbp[e];
+                        paa[q & 1] += ra[q] * ra[q];
+                        pbb[q & 1] += y * y;
+                        pab[q & 1] += ra[q] * y;
+                    }
+                }
+                double saa = paa[0] + paa[1], sbb = pbb[0] + pbb[1], sab = pab[0] + pab[1];
+#ifndef TTIPM_EMU
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    saa += __shfl_xor_sync(0xffffffffu, saa, o);
+                    sbb += __shfl_xor_sync(0xffffffffu, sbb, o);
+                    sab += __shfl_xor_sync(0xffffffffu, sab, o);
+                }
+#else
+                saa = warp_sum(saa);
+                sbb = warp_sum(sbb);
+                sab = warp_sum(sab);
+#endif
+                if (sab * sab > tol2 * saa * sbb && fmin(saa, sbb) > floor2) {
+                    double cs, sn;
+                    lin_rotation(saa, sbb, sab, cs, sn);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const int e = lane + 32 * q;
+                        const double x = ra[q], y = RB_REGS ? rb[q] : (e < Ls ? rbp[e] : 0.0);
+                        ra[q] = cs * x - sn * y;
+                        if (e < Ls) rbp[e] = sn * x + cs * y;
+                    }
+                    rot = true;
+                }
+            }
+            __syncthreads();
+        }
+        if (have) {
+            double* rap = rowsS + (long)i * ldg;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int e = lane + 32 * q;
+                if (e < Ls) rap[e] = ra[q];
+            }
+        }
+    }
+    return rot;
 }
 
 // (eps * ||G||_F)^2 of the K x K matrix G (row stride ldg, global memory), computed redundantly by every CTA
@@ -397,6 +535,7 @@ TT_DEV double lin_noise_floor2(LinCtx& c, const double* G, int K, int ldg) {
 
 // block one-sided Jacobi on the K rows [G | Jt | pad] of GJ (row stride ldg, row-major, global memory).
 // Ends with a grid barrier (all rows globally visible).  Returns the number of sweeps.
+template <int NT>
 TT_DEV int lin_jacobi(LinCtx& c, double* GJ, int K, int Mj, int* flags, long long* tm) {
     const int nb = c.p.nb, ldg = c.p.ldg, Ls = K + Mj, lane = c.lane, wid = c.wid, nw = c.nw;
     const int nblk = (K + nb - 1) / nb, nbe = nblk + (nblk & 1), npairs = nbe / 2, rounds = nbe - 1;
@@ -460,13 +599,20 @@ TT_DEV int lin_jacobi(LinCtx& c, double* GJ, int K, int Mj, int* flags, long lon
                     }
                 }
                 if (bvalid) {
-                    for (int u = 0; u < nb; ++u) {
-                        for (int i = wid; i < nb; i += nw) {
-                            const int jb = (i + u) % nb;
-                            if (i >= na || jb >= nbb) continue;
-                            rot |= lin_jacobi_pair(rowsS + (long)i * ldg, rowsS + (long)(nb + jb) * ldg, K, Ls, tol2, floor2, lane);
+                    if (Ls <= 128) rot |= lin_cross_pairs_reg<4, true>(rowsS, nb, na, nbb, K, Ls, ldg, tol2, floor2, lane, wid, nw);
+                    else if (Ls <= 256) rot |= lin_cross_pairs_reg<8, true>(rowsS, nb, na, nbb, K, Ls, ldg, tol2, floor2, lane, wid, nw);
+                    else if (Ls <= 384) rot |= lin_cross_pairs_reg<12, true>(rowsS, nb, na, nbb, K, Ls, ldg, tol2, floor2, lane, wid, nw);
+                    else if (NT <= 384 && Ls <= 512) rot |= lin_cross_pairs_reg<NT <= 384 ? 16 : 1, true>(rowsS, nb, na, nbb, K, Ls, ldg, tol2, floor2, lane, wid, nw);
+                    else if (NT <= 384 && Ls <= 704) rot |= lin_cross_pairs_reg<NT <= 384 ? 22 : 1, false>(rowsS, nb, na, nbb, K, Ls, ldg, tol2, floor2, lane, wid, nw);
+                    else {
+                        for (int u = 0; u < nb; ++u) {
+                            for (int i = wid; i < nb; i += nw) {
+                                const int jb = (i + u) % nb;
+                                if (i >= na || jb >= nbb) continue;
+                                rot |= lin_jacobi_pair(rowsS + (long)i * ldg, rowsS + (long)(nb + jb) * ldg, K, Ls, tol2, floor2, lane);
+                            }
+                            __syncthreads();
                         }
-                        __syncthreads();
                     }
                 }
                 if (rot && lane == 0) *rotated = 1;
@@ -485,8 +631,10 @@ TT_DEV int lin_jacobi(LinCtx& c, double* GJ, int K, int Mj, int* flags, long lon
             }
             const long long t3 = lin_now();
             fence_proxy_async();               // rows written through the generic proxy are read by bulk copies next round
+            const long long t4 = lin_now();
             c.sync();
-            tm[3] += lin_now() - t3;
+            tm[2] += t4 - t3;
+            tm[3] += lin_now() - t4;
         }
         if (ld_cg_i(&flags[sweeps]) == 0) {
             ++sweeps;
@@ -642,7 +790,7 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
     fence_proxy_async();
     c.sync();
     const long long t_q = lin_now();
-    const int sweeps = p.resident ? lin_jacobi_resident(c, G, K, Mj) : lin_jacobi(c, G, K, Mj, flags, tm);
+    const int sweeps = p.resident ? lin_jacobi_resident(c, G, K, Mj) : lin_jacobi<NT>(c, G, K, Mj, flags, tm);
     const long long t_jac = lin_now();
     // singular values = row norms
     for (int i = c.gw; i < K; i += c.GW) {
@@ -695,6 +843,10 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
         info[9] = (int)tm[3];
         info[10] = (int)(lin_now() - t_start);
         info[11] = p.cluster;
+        info[12] = (int)c.tq[0];
+        info[13] = (int)c.tq[1];
+        info[14] = (int)c.tq[2];
+        info[15] = (int)c.tq[3];
     }
 }
 
@@ -704,6 +856,7 @@ static double g_floor_factor = 0.0;
 static int g_tall_triple_qr = 1;
 static int g_coop_threads = 256;
 static int g_use_cluster = 1;
+static int g_wide_cta_min_dim = 96;
 
 struct LinPlan {
     LinParams p;
@@ -795,8 +948,35 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
     if (p.resident && K > 16) pl.threads = 2 * block_threads();
 #else
     if (p.resident && K > 16) pl.threads = 512;
+    if (G > 1 && (nb > 8 || K >= g_wide_cta_min_dim)) pl.threads = 512;     // a warp per block row / trailing column
+    // rows longer than 384 doubles: 16 / 22 register chunks per row need the 384-thread build of the kernel (170 registers)
+    if (G > 1 && !p.resident && mode == 0 && ldg > 384 && ldg <= 704 && nb <= 12) pl.threads = 384;
 #endif
     return 0;
+}
+
+template <int NT>
+static int lin_launch_t(LinPlan& pl, int nbatch, tt_stream_t st) {
+    LinParams& p = pl.p;
+    int G = pl.grid;
+    if (G > 1 && g_use_cluster &&
+        cluster_launch_possible(k_linalg<NT>, G, nbatch, dim3(pl.threads), (size_t)pl.smem_bytes)) {
+        p.cluster = 1;
+        return launch_kernel_cluster("k_linalg", k_linalg<NT>, dim3(G, nbatch), dim3(pl.threads), (size_t)pl.smem_bytes, st, p);
+    }
+#ifndef TTIPM_EMU
+    if (G > 1) {
+        DevInfo di = dev_info();
+        cudaFuncSetAttribute((const void*)k_linalg<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linalg<NT>, pl.threads, (size_t)pl.smem_bytes);
+        if (per_sm < 1) return fail(4, "linalg: kernel does not fit on an SM with %ld B shared memory", pl.smem_bytes);
+        if (G > per_sm * di.sms) G = per_sm * di.sms;
+    }
+#endif
+    if (G > 1)
+        return launch_kernel("k_linalg", k_linalg<NT>, dim3(G, nbatch), dim3(pl.threads), (size_t)pl.smem_bytes, st, true, p);
+    return launch_kernel("k_linalg", k_linalg<NT>, dim3(1, nbatch), dim3(pl.threads), (size_t)pl.smem_bytes, st, false, p);
 }
 
 static int lin_launch(int mode, const double* A, long a_rs, long a_cs, long a_bs, int M, int N, double* U, double* S,
@@ -809,25 +989,8 @@ static int lin_launch(int mode, const double* A, long a_rs, long a_cs, long a_bs
     p.U = U; p.S = S; p.Wt = Wt; p.info = info; p.ws = ws;
     if (((uintptr_t)ws & 15) != 0) return fail(1, "linalg: workspace must be 16-byte aligned");
     if (dev_memset(ws, 0, (size_t)nbatch * 40 * 8, st)) return fail(5, "linalg: memset failed");
-    int G = pl.grid;
-    if (G > 1 && g_use_cluster &&
-        cluster_launch_possible(k_linalg<512>, G, nbatch, dim3(pl.threads), (size_t)pl.smem_bytes)) {
-        p.cluster = 1;
-        return launch_kernel_cluster("k_linalg", k_linalg<512>, dim3(G, nbatch), dim3(pl.threads), (size_t)pl.smem_bytes, st, p);
-    }
-#ifndef TTIPM_EMU
-    if (G > 1) {
-        DevInfo di = dev_info();
-        cudaFuncSetAttribute((const void*)k_linalg<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linalg<512>, pl.threads, (size_t)pl.smem_bytes);
-        if (per_sm < 1) return fail(4, "linalg: kernel does not fit on an SM with %ld B shared memory", pl.smem_bytes);
-        if (G > per_sm * di.sms) G = per_sm * di.sms;
-    }
-#endif
-    if (G > 1)
-        return launch_kernel("k_linalg", k_linalg<512>, dim3(G, nbatch), dim3(pl.threads), (size_t)pl.smem_bytes, st, true, p);
-    return launch_kernel("k_linalg", k_linalg<512>, dim3(1, nbatch), dim3(pl.threads), (size_t)pl.smem_bytes, st, false, p);
+    if (pl.threads == 384) return lin_launch_t<384>(pl, nbatch, st);
+    return lin_launch_t<512>(pl, nbatch, st);
 }
 
 }  // namespace ttipm
@@ -849,6 +1012,7 @@ extern "C" int ttipm_linalg_use_cluster(int on) {
 extern "C" int ttipm_linalg_threads(int threads) {
     const int old = g_coop_threads;
     if (threads == 256 || threads == 512) g_coop_threads = threads;
+    g_wide_cta_min_dim = threads == 256 ? (1 << 30) : 96;           // 256: never widen (tuning runs)
     return old;
 }
 

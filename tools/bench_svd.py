@@ -57,7 +57,8 @@ def run(rt, a, coop, iters=5):
         inf = info.cpu().numpy().tolist()
         return dict(M=M, N=N, coop=coop, ms=ms, sweeps=inf[0], qr_us=inf[1] / 1e3, q_us=inf[2] / 1e3, jac_us=inf[3] / 1e3,
                     grid=inf[4], nb=inf[5], jac_load_us=inf[6] / 1e3, jac_rot_us=inf[7] / 1e3, jac_store_us=inf[8] / 1e3,
-                    jac_sync_us=inf[9] / 1e3, total_us=inf[10] / 1e3, s_err=float(np.max(np.abs(Sh - sref)) / sref[0]),
+                    jac_sync_us=inf[9] / 1e3, total_us=inf[10] / 1e3, cluster=inf[11], qr_load_us=inf[12] / 1e3,
+                    qr_factor_us=inf[13] / 1e3, qr_trail_us=inf[14] / 1e3, qr_sync_us=inf[15] / 1e3, s_err=float(np.max(np.abs(Sh - sref)) / sref[0]),
                     rec=float(np.linalg.norm(Uh @ Wh - a) / np.linalg.norm(a)),
                     orth=float(np.linalg.norm(Uh.T @ Uh - np.eye(K))))
     finally:
