@@ -34,7 +34,7 @@ sys.path.insert(0, HERE)
 import ref_env  # noqa: E402
 from run_ref_ipm import build_problem, load_config  # noqa: E402
 
-GOLD = os.path.abspath(os.path.join(HERE, "..", "..", "tests", "golden"))
+GOLD = os.environ.get("TTIPM_GOLD_DIR") or os.path.abspath(os.path.join(HERE, "..", "..", "tests", "golden"))
 
 
 def _rand_tt(rng, ranks, mode):
@@ -219,6 +219,47 @@ def als():
         print(name, "ranks", [c.shape[-1] for c in res[:-1]])
     np.savez_compressed(os.path.join(GOLD, "als_products.npz"), **out)
     print("wrote als_products.npz with", len(out), "arrays")
+
+
+def generators():
+    """Problem-generator helpers of src/tt_ops.py: seeded sampler outputs, triangular matrices,
+    bond splitting, and whole create_problem outputs as dense matrices.  generators.npz."""
+    ref = ref_env.load()
+    T = ref.tt_ops
+    out = {}
+    for seed, dim, rank in ((319, 5, 2), (83, 7, 4), (7, 3, 1), (11, 1, 2)):
+        np.random.seed(seed)
+        _put_tt(out, f"binary_sym/{seed}_{dim}_{rank}", T.tt_random_binary_sym(dim, rank, skew=-1.0))
+    for seed, dim, r in ((319, 5, 1), (41, 6, 1), (83, 6, 2)):
+        np.random.seed(seed)
+        g = T.tt_random_graph(dim, r)
+        out[f"graph/{seed}_{dim}_{r}/dense"] = T.tt_matrix_to_matrix(g)
+        out[f"graph/{seed}_{dim}_{r}/ranks"] = np.array(T.tt_ranks(g))
+        out[f"graph/{seed}_{dim}_{r}/rng_pos"] = np.array(np.random.get_state()[2])
+    for dim in (1, 2, 4):
+        _put_tt(out, f"tril/{dim}", T.tt_tril_one_matrix(dim))
+        _put_tt(out, f"triu/{dim}", T.tt_triu_one_matrix(dim))
+    rng = np.random.default_rng(5)
+    m = _rand_tt(rng, [3, 2, 3], (2, 2))
+    _put_tt(out, "split/in", m)
+    _put_tt(out, "split/out", T.tt_split_bonds(_cp(m)))
+    out["to_matrix"] = T.tt_matrix_to_matrix(m)
+    for name, dim, rank, seed in (("maxcut", 4, 1, 319), ("corr_clust", 4, 1, 208), ("max_stable_set", 3, 1, 876),
+                                  ("graphm", 2, 1, 5)):
+        np.random.seed(seed)
+        res = ref_env.create_problem(name, dim, rank)
+        out[f"problem/{name}/n"] = np.array(len(res))
+        for q, item in enumerate(res):
+            if item is None:
+                out[f"problem/{name}/{q}/none"] = np.array(1)
+            elif isinstance(item, dict):
+                for key, tt in item.items():
+                    _put_tt(out, f"problem/{name}/{q}/dict/{key}", tt)
+            else:
+                _put_tt(out, f"problem/{name}/{q}/tt", item)
+        out[f"problem/{name}/args"] = np.array([dim, rank, seed])
+    np.savez_compressed(os.path.join(GOLD, "generators.npz"), **out)
+    print("wrote generators.npz with", len(out), "arrays")
 
 
 class _Budget(BaseException):
@@ -429,6 +470,8 @@ if __name__ == "__main__":
              inputs_only="--inputs-only" in sys.argv)
     elif cmd == "als":
         als()
+    elif cmd == "generators":
+        generators()
     elif cmd == "eigen":
         eigen(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]),
               set(int(v) for v in sys.argv[6].split(",")))

@@ -501,6 +501,24 @@ struct Dense {
     }
     // LU factorisation (partial pivoting) of a row-major matrix in place; piv has m ints (stored in doubles)
     struct LU { Tensor a; Tensor piv; long m; };
+    std::vector<Tensor> lu_infos;      // device info words of the getrf calls of this solve (checked by lu_check)
+    // scipy's lu_factor / solve raise on an exactly singular factor (reference src/tt_ipm.py:204,215,320-326 -> the
+    // except branch sets direct_solve_failure): one read-back for all factorizations of the solve
+    void lu_check() {
+#ifndef TTIPM_EMU
+        for (const Tensor& t : lu_infos) {
+            double h;
+            to_host(c, t.p, 1, &h);
+            int hi;
+            memcpy(&hi, &h, sizeof(int));
+            if (hi != 0) {
+                lu_infos.clear();
+                throw DriverError(94, "local Schur complement is singular (getrf info > 0)");
+            }
+        }
+#endif
+        lu_infos.clear();
+    }
     LU lu_factor(const Tensor& A, long m) {
         LU f;
         f.m = m;
@@ -517,6 +535,7 @@ struct Dense {
             piv[k] = (int)best;
             if (best != k)
                 for (long j = 0; j < m; ++j) std::swap(a[k * m + j], a[best * m + j]);
+            if (a[k * m + k] == 0.0) throw DriverError(94, "local Schur complement is singular");
             for (long i = k + 1; i < m; ++i) {
                 a[i * m + k] /= a[k * m + k];
                 for (long j = k + 1; j < m; ++j) a[i * m + j] -= a[i * m + k] * a[k * m + j];
@@ -527,9 +546,11 @@ struct Dense {
         int lwork = 0;
         cusolverDnDgetrf_bufferSize(sol, (int)m, (int)m, f.a.p, (int)m, &lwork);
         Tensor work = Tensor::empty(c, {(long)lwork + 2});
-        int* info = (int*)(work.p + lwork);
+        Tensor info_t = Tensor::empty(c, {2});
+        int* info = (int*)info_t.p;
         if (cusolverDnDgetrf(sol, (int)m, (int)m, f.a.p, (int)m, work.p, (int*)f.piv.p, info) != CUSOLVER_STATUS_SUCCESS)
             throw DriverError(93, "getrf failed");
+        lu_infos.push_back(info_t);
         c.launches++;
 #endif
         return f;
@@ -590,7 +611,8 @@ struct Amen {
     double eps = 1e-12, trunc_tol = 0.0;
     bool direct_solve_failure = false;
     int sweeps = 0;
-    long local_solves = 0, lgmres_its = 0, lgmres_matvecs = 0, lgmres_calls = 0, dense_solves = 0;
+    long local_solves = 0, lgmres_its = 0, lgmres_matvecs = 0, lgmres_calls = 0, dense_solves = 0, krylov_failures = 0;
+    std::string last_krylov_error;
     std::vector<double> trace;                 // (swp, k, res_old, res_new, r*R) per local solve
     std::unique_ptr<Dense> dense;
     std::vector<Tensor> lg_infos;              // device info blocks of the Krylov solves (read lazily)
@@ -786,6 +808,7 @@ struct Amen {
             D.chol_solve(Lc.p, m, xx.p, 1);
             put(1, xx);
         }
+        D.lu_check();
         dense_solves++;
         return sol;
     }
@@ -854,6 +877,7 @@ struct Amen {
             std::vector<double> nn = host_sums(c, {&n0, &n1});
             const bool use_prev = sqrt(nn[1]) < sqrt(nn[0]);
             Tensor info = Tensor::empty(c, {6});
+            bool krylov_failed = false;
             LgProf pr;
             pr.nv = (double)nred * m;
             pr.restart = restart;
@@ -870,10 +894,33 @@ struct Amen {
                 cudaEventRecord(pr.e0, c.st);
             }
 #endif
-            Tensor xs = lg(use_prev ? diff : lrhs, false, &info);
+            Tensor xs;
+            try {
+                xs = lg(use_prev ? diff : lrhs, false, &info);
+            } catch (const DriverError& e) {
+                // the reference catches every exception of the local solve, keeps previous_solution and flags
+                // direct_solve_failure (src/tt_ipm.py:262-280, :379-399); the sweep goes on and the restart ladder of
+                // tt_restarted_block_amen decides
+                krylov_failures++;
+                last_krylov_error = e.what();
+                krylov_failed = true;
+            }
 #ifndef TTIPM_EMU
             if (profile) cudaEventRecord(pr.e1, c.st);
 #endif
+            if (krylov_failed) {
+#ifndef TTIPM_EMU
+                if (profile) {
+                    cudaEventDestroy(pr.e0);
+                    cudaEventDestroy(pr.e1);
+                }
+#endif
+                o.sol = prev;
+                o.res_new = o.res_old;
+                direct_solve_failure = true;
+                local_solves++;
+                return o;
+            }
             lg_prof.push_back(pr);
             lg_infos.push_back(info);
             lgmres_calls++;
@@ -894,8 +941,8 @@ struct Amen {
         block_matvec(c, full, o.sol, false, bs, r, R, &o.rhs, 1.0, -1.0, &new_ss);
         std::vector<double> s2 = host_sums(c, {&new_ss});
         const double res_new = sqrt(s2[0]) / o.norm_rhs;
-        if (o.res_old < res_new) o.sol = prev;
-        o.res_new = std::min(o.res_old, res_new);
+        if (!(res_new <= o.res_old)) o.sol = prev;           // also keeps prev when res_new is not finite
+        o.res_new = std::isfinite(res_new) ? std::min(o.res_old, res_new) : o.res_old;
         direct_solve_failure = direct_fail;
         local_solves++;
         return o;
@@ -1150,6 +1197,7 @@ struct ttipm_amen {
     }
 
 extern "C" ttipm_amen* ttipm_amen_create(int d, int block_size, int ineq, void* stream) {
+    if (check_bound_device()) return nullptr;          // process-wide handles / staging belong to one device
     pool_keep_freed_blocks();
     ttipm_amen* h = new ttipm_amen();
     h->a.c.st = (tt_stream_t)stream;

@@ -60,7 +60,7 @@ void pool_keep_freed_blocks() {
 }
 
 DevInfo dev_info() {
-    static DevInfo cached = {0, 0};
+    static DevInfo cached = {0, 0, 0};
     if (cached.sms) return cached;
 #ifdef TTIPM_EMU
     const char* s = getenv("TTIPM_EMU_SMS");
@@ -69,10 +69,23 @@ DevInfo dev_info() {
 #else
     int dev = 0;
     cudaGetDevice(&dev);
+    cached.dev = dev;
     cudaDeviceGetAttribute(&cached.sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&cached.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
 #endif
     return cached;
+}
+
+int check_bound_device() {
+#ifndef TTIPM_EMU
+    const DevInfo di = dev_info();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != di.dev)
+        return fail(6, "libttipm_b200 is bound to CUDA device %d (first use) but the current device is %d: use one process per GPU",
+                    di.dev, dev);
+#endif
+    return 0;
 }
 
 int block_threads() {

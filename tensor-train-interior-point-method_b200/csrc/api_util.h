@@ -13,8 +13,12 @@ namespace ttipm {
 struct DevInfo {
     int sms;
     int smem_optin;
+    int dev;       // ordinal of the device the process-wide state (handles, opt-ins, staging, this cache) is bound to
 };
 DevInfo dev_info();
+// The library keeps process-wide state bound to ONE device (one process per GPU, as torch.distributed launches it):
+// 0 if the calling thread's current device is that device, else an error through fail().
+int check_bound_device();
 void pool_keep_freed_blocks();
 int block_threads();
 int dev_memset(void* p, int v, size_t bytes, tt_stream_t st);

@@ -723,6 +723,7 @@ extern "C" int ttipm_local_lgmres(int ineq, const ttipm_term* K00, const ttipm_t
     p.mode = apply_only ? LG_APPLY : LG_SOLVE;
     tt_stream_t st = (tt_stream_t)stream;
     if (dev_memset(p.ctrl_d, 0, 32 * 8, st)) return fail(5, "lgmres: memset failed");
+    if (check_bound_device()) return 6;                 // the shared-memory opt-in below is per device
 #ifndef TTIPM_EMU
     {   // the cooperative grid must be co-resident
         static int optin_done = 0;

@@ -370,6 +370,8 @@ class NativeBlockAmen:
         self.d = len(model)
         self.x_shape = tuple(model[0].shape[1:-1])
         self.h = C.c_void_p(self.lib.ttipm_amen_create(self.d, self.block_size, int(self.ineq), self.rt.stream()))
+        if not self.h.value:
+            raise RuntimeError("ttipm_amen_create failed: " + self.lib.ttipm_last_error().decode())
         self._keep = []
         for (i, j), cores in block_A.items():
             for k, c in enumerate(cores):

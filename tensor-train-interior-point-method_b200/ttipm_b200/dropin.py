@@ -34,7 +34,8 @@ def install(prefixes=("src", "cy_src", "psd_system", "refproblem_")):
         table[name] = getattr(lgmres, name)
     done = {}
     for modname, mod in list(sys.modules.items()):
-        if mod is None or not any(modname == p or modname.startswith(p + ".") or modname.startswith(p) for p in prefixes):
+        if mod is None or not any(modname == p or modname.startswith(p + ".") or
+                                  (p.endswith("_") and modname.startswith(p)) for p in prefixes):
             continue
         if modname.startswith("ttipm_b200"):
             continue

@@ -52,10 +52,18 @@ def tt_swap_all(tt):
     return [np.swapaxes(c, 0, -1) for c in reversed(tt)]
 
 
+def tt_merge_cores(tt):
+    """src/tt_ops.py:335-339: neighbouring cores pairwise into one core whose modes interleave as (i s) resp.
+    (i s, j d).  Host NumPy: only the problem generators reach it (psd_system/max_stable_set, graphm), on tiny cores."""
+    if tt[0].ndim == 3:
+        return [np.einsum("kir,rsK->kisK", a, b) for a, b in zip(tt[:-1:2], tt[1::2])]
+    return [np.einsum("kijr,rsdK->kisjdK", a, b) for a, b in zip(tt[:-1:2], tt[1::2])]
+
+
 def tt_reshape(tt, shape):
-    """src/tt_ops.py:330-333 (the core-merging branch is unused by the IPM path)."""
+    """src/tt_ops.py:330-333."""
     if np.prod(shape) > np.prod(tt[0].shape[1:-1]):
-        raise NotImplementedError("tt_reshape with core merging (src/tt_ops.py:335-339) is off the IPM path")
+        tt = tt_merge_cores(tt)
     return [c.reshape(c.shape[0], *shape, c.shape[-1]) for c in tt]
 
 

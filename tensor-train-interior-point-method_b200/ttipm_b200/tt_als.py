@@ -295,7 +295,7 @@ def tt_block_amen(block_A, block_b, term_tol, r_max=100, eps=1e-12, nswp=22, x0=
     dev = driver(block_A._data, block_A._aliases, block_A._transposes, block_b._data, ineq, stats=_stats)
     x, res = dev.solve(term_tol, r_max=r_max, eps=eps, nswp=nswp, x0=x0, kick_rank=kick_rank, amen=amen)
     if verbose:
-        print(f"\\tSolution rank is {dev.ranks}\\n\\tResidual {res:.3e}\\n\\tNumber of sweeps {dev.sweeps}", flush=True)
+        print(f"\tSolution rank is {dev.ranks}\n\tResidual {res:.3e}\n\tNumber of sweeps {dev.sweeps}", flush=True)
     return x, res
 
 
@@ -316,7 +316,7 @@ def tt_restarted_block_amen(block_A, block_b, rank_restriction, op_tol, terminat
 
     orig_rhs_norm = block_b.norm
     if orig_rhs_norm < 0.5 * op_tol:
-        raise RuntimeError(f"\\n\\tAbsolute tolerance already reached: {orig_rhs_norm:4f} < {op_tol:4f}")
+        raise RuntimeError(f"\n\tAbsolute tolerance already reached: {orig_rhs_norm:4f} < {op_tol:4f}")
     x_cores, res = solve_als(rank_restriction, x0, 2)
     if res < termination_tol:
         return x_cores, res
@@ -330,5 +330,5 @@ def tt_restarted_block_amen(block_A, block_b, rank_restriction, op_tol, terminat
         rhs_norm = residual_norm(x_cores)
         if rhs_norm < termination_tol * orig_rhs_norm or rhs_norm < orig_rhs_norm:
             return x_cores, res
-    raise RuntimeError(f"\\n\\tNumber of restarts exhausted, Relative Error = {rhs_norm / orig_rhs_norm:3e}. "
+    raise RuntimeError(f"\n\tNumber of restarts exhausted, Relative Error = {rhs_norm / orig_rhs_norm:3e}. "
                        "Consider increasing rank ceiling.")
