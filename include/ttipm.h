@@ -240,6 +240,39 @@ int ttipm_amen_profile(ttipm_amen* h, double* out);
  * algorithmic flops; trace: 5 doubles (swp, k, res_old, res_new, r*R) per solve */
 int ttipm_amen_stats(ttipm_amen* h, double* stats, double* trace, int max_trace_rows);
 
+/* ---- step-size eigen sweeps: local problems of tt_max_generalised_eigen / tt_min_eig ---------------
+ * One- or two-site projection of a TT matrix onto the current interfaces,
+ *   'lsr,smnk,kptS,LSR->lmpLrntR' (reference src/tt_als.py:952-959, :1305) or, with A2 == NULL,
+ *   'lsr,smnS,LSR->lmLrnR' (:1037-1041, :1346),
+ * as a dense (l n1 n2 L)^2 row-major matrix; symmetrise != 0 stores 0.5 (M + M^T) like the reference does. */
+typedef struct ttipm_eig_op {
+    const double* P1;      /* (l, s, l)       */
+    const double* A1;      /* (s, n1, n1, k)  */
+    const double* A2;      /* (k, n2, n2, S) or NULL */
+    const double* P2;      /* (L, S, L)       */
+    int64_t p1_strides[3], a1_strides[4], a2_strides[4], p2_strides[3];
+    int32_t l, s, k, S, L, n1, n2;
+} ttipm_eig_op;
+int ttipm_eig_assemble(const ttipm_eig_op* op, int symmetrise, double* out, void* stream);
+/* doubles of workspace for ttipm_eig_lanczos / ttipm_eig_gen_largest with a Lanczos basis of K vectors */
+int64_t ttipm_eig_workspace(int m, int K);
+/* Extreme eigenpair of cA * A + cD * D (dense symmetric m x m; D may be NULL): smallest algebraic (largest == 0) or
+ * largest (largest != 0).  Replaces scipy.sparse.linalg.eigsh(M, k=1, which="SA", v0=...) / lobpcg of the reference
+ * (src/tt_als.py:962-981, :1003-1006, :1307, :1320).  v0 (may be NULL) is the start vector; x receives the unit
+ * eigenvector; out[10] = eigenvalue, residual ||M x - lambda x||, matvecs, converged flag, v0^T M v0 and
+ * ||M v0 - (v0^T M v0) v0|| of the RAW start vector (the reference's `eig_val` / `old_res`, :992-993), cycles, ||v0||,
+ * ||M v0 - lambda v0|| (tt_min_eig's old_res, :1315), reserved.
+ * max_cycles == 0 only evaluates the start-vector quantities.  One persistent launch (a thread-block cluster). */
+int ttipm_eig_lanczos(const double* A, double cA, const double* D, double cD, int m, const double* v0, int largest,
+                      int K, int max_cycles, double tol, double* x, double* out, double* ws, void* stream);
+/* Largest eigenpair of (-D) x = lambda A x, A positive definite (reference eigsh(-D, M=A, which="LA"),
+ * src/tt_als.py:985, :1071); out[0] = lambda, out[3] = 0 if A is not positive definite (the reference's exception
+ * branch).  Cholesky reduction through cuSOLVER / cuBLAS, then the kernel above. */
+int ttipm_eig_gen_largest(const double* A, const double* D, int m, const double* v0, int K, int max_cycles, double tol,
+                          double* x, double* out, double* ws, void* stream);
+/* tuning / tests: force the number of CTAs of the Lanczos kernel's cluster (0 = automatic) */
+int ttipm_eig_force_cluster(int ctas);
+
 #ifdef __cplusplus
 }
 #endif

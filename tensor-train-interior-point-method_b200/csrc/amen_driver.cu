@@ -398,9 +398,6 @@ static int prune_singular_vals(const std::vector<double>& s, double eps) {   // 
 // dense Schur fallback: cuSOLVER / cuBLAS on row-major device matrices (reference src/tt_ipm.py:196-223, :298-334)
 // ---------------------------------------------------------------------------------------------------
 #ifndef TTIPM_EMU
-// library handles are expensive to create (tens of ms): one pair per process, re-bound to the caller's stream
-static cublasHandle_t g_blas = nullptr;
-static cusolverDnHandle_t g_sol = nullptr;
 #endif
 struct Dense {
     Ctx& c;
@@ -410,12 +407,10 @@ struct Dense {
 #endif
     explicit Dense(Ctx& ctx) : c(ctx) {
 #ifndef TTIPM_EMU
-        if (!g_blas && cublasCreate(&g_blas) != CUBLAS_STATUS_SUCCESS) throw DriverError(93, "cublasCreate failed");
-        if (!g_sol && cusolverDnCreate(&g_sol) != CUSOLVER_STATUS_SUCCESS) throw DriverError(93, "cusolverDnCreate failed");
-        blas = g_blas;
-        sol = g_sol;
-        cublasSetStream(blas, c.st);
-        cusolverDnSetStream(sol, c.st);
+        blas = (cublasHandle_t)blas_handle(c.st);          // one pair per process (api.cu), re-bound to this stream
+        sol = (cusolverDnHandle_t)solver_handle(c.st);
+        if (!blas) throw DriverError(93, "cublasCreate failed");
+        if (!sol) throw DriverError(93, "cusolverDnCreate failed");
 #endif
     }
     ~Dense() {}

@@ -76,6 +76,35 @@ DevInfo dev_info() {
     return cached;
 }
 
+#ifndef TTIPM_EMU
+}  // namespace ttipm
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+namespace ttipm {
+// library handles are expensive to create (tens of ms): one pair per process, re-bound to the caller's stream
+void* blas_handle(tt_stream_t st) {
+    static cublasHandle_t h = nullptr;
+    if (!h && cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) {
+        h = nullptr;
+        return nullptr;
+    }
+    cublasSetStream(h, st);
+    return (void*)h;
+}
+void* solver_handle(tt_stream_t st) {
+    static cusolverDnHandle_t h = nullptr;
+    if (!h && cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) {
+        h = nullptr;
+        return nullptr;
+    }
+    cusolverDnSetStream(h, st);
+    return (void*)h;
+}
+#else
+void* blas_handle(tt_stream_t) { return nullptr; }
+void* solver_handle(tt_stream_t) { return nullptr; }
+#endif
+
 int check_bound_device() {
 #ifndef TTIPM_EMU
     const DevInfo di = dev_info();

@@ -19,6 +19,9 @@ DevInfo dev_info();
 // The library keeps process-wide state bound to ONE device (one process per GPU, as torch.distributed launches it):
 // 0 if the calling thread's current device is that device, else an error through fail().
 int check_bound_device();
+// process-wide cuBLAS / cuSOLVER handles (cublasHandle_t / cusolverDnHandle_t as void*), re-bound to `st`; nullptr on failure
+void* blas_handle(tt_stream_t st);
+void* solver_handle(tt_stream_t st);
 void pool_keep_freed_blocks();
 int block_threads();
 int dev_memset(void* p, int v, size_t bytes, tt_stream_t st);

@@ -25,6 +25,12 @@ class RhsTerm(C.Structure):
                 ("b", i32), ("Bp", i32)]
 
 
+class EigOp(C.Structure):
+    _fields_ = [("P1", C.c_void_p), ("A1", C.c_void_p), ("A2", C.c_void_p), ("P2", C.c_void_p),
+                ("p1_strides", i64 * 3), ("a1_strides", i64 * 4), ("a2_strides", i64 * 4), ("p2_strides", i64 * 3),
+                ("l", i32), ("s", i32), ("k", i32), ("S", i32), ("L", i32), ("n1", i32), ("n2", i32)]
+
+
 SIGNATURES = {
     "ttipm_abi_version": (C.c_int, []),
     "ttipm_last_error": (C.c_char_p, []),
@@ -82,6 +88,13 @@ SIGNATURES = {
     "ttipm_linalg_tall_triple_qr": (C.c_int, [C.c_int]),
     "ttipm_linalg_threads": (C.c_int, [C.c_int]),
     "ttipm_linalg_use_cluster": (C.c_int, [C.c_int]),
+    "ttipm_eig_assemble": (C.c_int, [C.POINTER(EigOp), C.c_int, C.c_void_p, C.c_void_p]),
+    "ttipm_eig_workspace": (i64, [C.c_int, C.c_int]),
+    "ttipm_eig_lanczos": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ttipm_eig_gen_largest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ttipm_eig_force_cluster": (C.c_int, [C.c_int]),
     "ttipm_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, i64, i64, i64, C.c_void_p, i64, i64,
                              i64, C.c_double, C.c_void_p, i64, i64, i64, C.c_int, C.c_void_p]),
 }

@@ -7,7 +7,7 @@
 After install(), src.tt_ipm.tt_ipm and psd_system/*/create_problem drive the CUDA path: every module
 whose namespace holds one of the reference's hot-path callables (the reference spreads them with
 `from src.tt_ops import *`) gets that name rebound to the ttipm_b200 implementation of the same
-signature.  The step-size eigen sweeps and everything else stay the reference's own code.
+signature (the step-size eigen sweeps of SURVEY 8f-1 included).  Everything else stays the reference's own code.
 """
 import sys
 
@@ -18,7 +18,7 @@ TT_OPS = ["tt_add", "tt_sub", "tt_scale", "tt_inner_prod", "tt_norm", "tt_normal
           "tt_fast_mat_mat_mul", "tt_fast_hadamard", "tt_IkronM", "tt_MkronI", "tt_diag", "tt_diag_op",
           "tt_entrywise_sum", "tt_rank_retraction", "tt_rl_orthogonalise_py", "tt_sum", "prune_singular_vals"]
 TT_ALS = ["tt_restarted_block_amen", "tt_block_amen", "tt_mat_vec_mul", "tt_mat_mat_mul", "tt_approx_mat_vec_mul",
-          "tt_approx_mat_mat_mul", "TTBlockMatrix",
+          "tt_approx_mat_mat_mul", "tt_max_generalised_eigen", "tt_min_eig", "TTBlockMatrix",
           "TTBlockVector", "compute_phi_bck_A", "compute_phi_fwd_A", "compute_phi_bck_rhs", "compute_phi_fwd_rhs"]
 LGMRES = ["MatVecWrapper", "IneqMatVecWrapper"]
 

@@ -436,3 +436,63 @@ def scale_cols(M, s, divide=False, rt=None):
 
 def scale_rows(M, s, divide=False, rt=None):
     return _scale2d(M, s, 0, divide, rt)
+
+
+# ---- local eigenvalue problems of the step-size sweeps ----------------------------------------------
+def eig_assemble(P1, A1, A2, P2, symmetrise=True, rt=None):
+    """Dense projection 'lsr,smnk,kptS,LSR->lmpLrntR' (A2 None: 'lsr,smnS,LSR->lmLrnR') as an (m, m) matrix,
+    0.5 (M + M^T) if symmetrise (reference src/tt_als.py:952-959, :1037-1041, :1305, :1346)."""
+    rt = rt or get_runtime()
+    op = _cabi.EigOp()
+    op.P1, op.A1, op.P2 = P1.data_ptr(), A1.data_ptr(), P2.data_ptr()
+    op.A2 = A2.data_ptr() if A2 is not None else None
+    op.p1_strides[:] = list(P1.stride())
+    op.a1_strides[:] = list(A1.stride())
+    op.a2_strides[:] = list(A2.stride()) if A2 is not None else [0, 0, 0, 0]
+    op.p2_strides[:] = list(P2.stride())
+    l, s, L = P1.shape[0], A1.shape[0], P2.shape[0]
+    n1 = A1.shape[1]
+    if A2 is not None:
+        k, n2, S = A1.shape[3], A2.shape[1], A2.shape[3]
+    else:
+        k, n2, S = A1.shape[3], 1, A1.shape[3]
+    assert P1.shape == (l, s, l) and P2.shape == (L, S, L), (P1.shape, A1.shape, P2.shape)
+    op.l, op.s, op.k, op.S, op.L, op.n1, op.n2 = l, s, k, S, L, n1, n2
+    m = l * n1 * n2 * L
+    out = rt.empty(m, m)
+    rt.check(rt.lib.ttipm_eig_assemble(C.byref(op), int(symmetrise), _ptr(out), rt.stream()), "ttipm_eig_assemble")
+    return out
+
+
+def _eig_ws(rt, m, K):
+    n = int(rt.lib.ttipm_eig_workspace(m, K))
+    if n <= 0:
+        raise rt_error(rt, f"ttipm_eig_workspace({m}, {K})")
+    return rt.empty(n)
+
+
+def eig_lanczos(A, cA=1.0, D=None, cD=0.0, v0=None, largest=False, K=64, max_cycles=30, tol=1e-9, rt=None):
+    """Extreme eigenpair of cA A + cD D (dense symmetric).  Returns (x device vector, out device[10]):
+    out = eigenvalue, residual, matvecs, converged, v0^T M v0, ||M v0 - (v0^T M v0) v0||, cycles, ||v0||,
+    ||M v0 - eigenvalue v0||, reserved."""
+    rt = rt or get_runtime()
+    m = A.shape[0]
+    K = max(2, min(K, m))
+    x, out = rt.empty(m), rt.zeros(10)
+    ws = _eig_ws(rt, m, K)
+    rt.check(rt.lib.ttipm_eig_lanczos(_ptr(A), float(cA), _ptr(D), float(cD), m, _ptr(v0), int(largest), K,
+                                      int(max_cycles), float(tol), _ptr(x), _ptr(out), _ptr(ws), rt.stream()),
+             "ttipm_eig_lanczos")
+    return x, out
+
+
+def eig_gen_largest(A, D, v0=None, K=64, max_cycles=30, tol=1e-9, rt=None):
+    """Largest eigenpair of (-D) x = lambda A x (A positive definite); out[3] == 0 if A is not positive definite."""
+    rt = rt or get_runtime()
+    m = A.shape[0]
+    K = max(2, min(K, m))
+    x, out = rt.empty(m), rt.zeros(10)
+    ws = _eig_ws(rt, m, K)
+    rt.check(rt.lib.ttipm_eig_gen_largest(_ptr(A), _ptr(D), m, _ptr(v0), K, int(max_cycles), float(tol), _ptr(x),
+                                          _ptr(out), _ptr(ws), rt.stream()), "ttipm_eig_gen_largest")
+    return x, out

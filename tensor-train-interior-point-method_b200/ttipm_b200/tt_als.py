@@ -16,6 +16,7 @@ from .runtime import get_runtime
 from .als_product import tt_approx_mat_mat_mul, tt_approx_mat_vec_mul  # noqa: F401  (reference src/tt_als.py:1502,1637)
 from .tt import tt_mat_mat_mul, tt_mat_vec_mul  # noqa: F401  (re-exported, reference src/tt_als.py:1631,1765)
 from .tt_ops import cached_einsum  # noqa: F401  (reference src/tt_als.py imports it from src.tt_ops)
+from .eigen import tt_max_generalised_eigen, tt_min_eig  # noqa: E402,F401  (reference src/tt_als.py:1132-1499)
 
 
 def _tt_get_block(i, block_matrix_tt):

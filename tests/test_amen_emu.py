@@ -97,7 +97,7 @@ def test_restarted_raises_on_tiny_rhs(rt):
 
 def test_dropin_rebinds_only_hot_path_names():
     """dropin.install() swaps the hot-path callables (SURVEY 8b names, incl. the ALS product pair) inside modules of a
-    reference-like tree and leaves everything else -- e.g. the step-size eigen sweeps (8f-1) -- alone"""
+    reference-like tree (the step-size eigen sweeps of 8f-1 included) and leaves everything else alone"""
     import sys
     import types
     from ttipm_b200 import dropin, tt, tt_als, lgmres
@@ -112,10 +112,11 @@ def test_dropin_rebinds_only_hot_path_names():
         done = dropin.install(prefixes=("refproblem_",))
         assert sorted(done["refproblem_fake"]) == sorted(
             ["tt_add", "tt_rank_reduce", "tt_mat_vec_mul", "tt_approx_mat_vec_mul", "tt_approx_mat_mat_mul",
-             "tt_restarted_block_amen", "TTBlockMatrix", "MatVecWrapper"])
+             "tt_restarted_block_amen", "TTBlockMatrix", "MatVecWrapper", "tt_min_eig", "tt_max_generalised_eigen"])
         assert mod.tt_add is tt.tt_add and mod.tt_approx_mat_vec_mul is tt_als.tt_approx_mat_vec_mul
         assert mod.TTBlockMatrix is tt_als.TTBlockMatrix and mod.MatVecWrapper is lgmres.MatVecWrapper
-        assert mod.tt_min_eig is sentinel and mod.tt_max_generalised_eigen is sentinel and mod.create_problem is sentinel
+        assert mod.tt_min_eig is tt_als.tt_min_eig and mod.tt_max_generalised_eigen is tt_als.tt_max_generalised_eigen
+        assert mod.create_problem is sentinel
         assert dropin.install(prefixes=("refproblem_",)).get("refproblem_fake") is None       # idempotent
     finally:
         del sys.modules["refproblem_fake"]
