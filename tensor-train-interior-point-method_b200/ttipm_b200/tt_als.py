@@ -295,6 +295,9 @@ def tt_block_amen(block_A, block_b, term_tol, r_max=100, eps=1e-12, nswp=22, x0=
     driver = DeviceBlockAmen if (_stats or {}).get("driver") == "python" else NativeBlockAmen
     dev = driver(block_A._data, block_A._aliases, block_A._transposes, block_b._data, ineq, stats=_stats)
     x, res = dev.solve(term_tol, r_max=r_max, eps=eps, nswp=nswp, x0=x0, kick_rank=kick_rank, amen=amen)
+    if _stats is not None:            # test / harness hook: one record per solve, the local-solve trace of all of them
+        _stats.setdefault("solves", []).append(dict(r_max=r_max, kick_rank=kick_rank, sweeps=dev.sweeps, res=float(res)))
+        _stats.setdefault("local_trace", []).extend([list(t) for t in dev.trace])
     if verbose:
         print(f"\tSolution rank is {dev.ranks}\n\tResidual {res:.3e}\n\tNumber of sweeps {dev.sweeps}", flush=True)
     return x, res
