@@ -39,7 +39,8 @@ for p in (os.path.join(ROOT, "tensor-train-interior-point-method_b200"), os.path
 
 WORKLOADS = {
     "maxcut_10": ("amen_maxcut_10_r1_s41_*.npz", "MaxCut dim 10 rank 1 seed 41 (configs/maxcut_10.yaml)"),
-    "maxcut_13": ("amen_maxcut_13_r2_s83_*.npz", "MaxCut dim 13 rank 2 seed 83 (configs/maxcut_13.yaml), IPM iteration 1"),
+    "maxcut_13": ("amen_maxcut_13_r2_s{seed}_*.npz", "MaxCut dim 13 rank 2 (configs/maxcut_13.yaml, seeds 83/45/23/53/12: one "
+                  "seed per GPU, seed 83 at N = 1), IPM iterations 0 (predictor, corrector) and 1 (predictor)"),
     "corr_clust_8": ("amen_corr_clust_8_r1_s208_*.npz", "Correlation clustering dim 8 rank 1 seed 208"),
     "max_stable_set_9": ("amen_max_stable_set_9_r1_s876_*.npz", "Max stable set dim 9 rank 1 seed 876"),
     "graphm_3": ("amen_graphm_3_r2_s256_*.npz", "Graph matching dim 3 rank 2 seed 256, IPM iteration 0"),
@@ -68,12 +69,20 @@ WORK_MODELS = {
 }
 
 
-def load_systems(workload):
+SEEDS = {"maxcut_13": [83, 45, 23, 53, 12]}           # configs/maxcut_13.yaml:2-7
+
+
+def load_systems(workload, replica=0):
+    """Traced KKT systems of one problem instance.  Workloads with several seeds deal them round-robin to the
+    replicas (BASELINE config 5: "all seeds, one seed per GPU"); replica 0 = the first seed."""
     import golden_io as G
     pat, _ = WORKLOADS[workload]
+    seeds = SEEDS.get(workload)
+    if seeds:
+        pat = pat.format(seed=seeds[replica % len(seeds)])
     files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", pat)))
     if not files:
-        raise SystemExit(f"no fixtures for workload {workload}")
+        raise SystemExit(f"no fixtures for workload {workload} ({pat})")
     return [G.load_amen(f) for f in files]
 
 
@@ -218,16 +227,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    systems = load_systems(args.workload)
+    nsys = len(load_systems(args.workload))
+    systems = []
+    for q in range(min(max(args.gpus, 1), len(SEEDS.get(args.workload, [0])))):     # the instances the GPU arm's replicas solve
+        systems += load_systems(args.workload, q)
     per_solve, cores, per, done = cpu_arm(systems, budget_s=150.0, passes=max(1, args.steps), warm=args.warmup > 0)
-    nsys = len(systems)
     line = {"impl": "reference", "metric": "tt_ipm_newton_system_solve_time", "value": per_solve, "unit": "s",
             "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": per_solve * nsys * 1e3,
             "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_config(args.workload, nsys), "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": per_solve, "unit": "s", "cores": cores, "kind": "port",
                              "seconds_per_solve_by_threads": {str(k): v for k, v in sorted(per.items())},
-                             "sample": f"{done} full pass(es) over the {nsys} system(s) with the NumPy/SciPy oracle port at each "
+                             "sample": f"{done} full pass(es) over the {len(systems)} system(s) with the NumPy/SciPy oracle port at each "
                                        "BLAS thread setting (the Python reference + PETSc cannot run on the GPU box); value = "
                                        "the fastest setting; bounded to ~150 s"},
             "e2e": {"value": per_solve, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -251,6 +262,45 @@ def measure_dgemm_peak(torch, dev):
         torch.cuda.synchronize(dev)
         best = min(best, e0.elapsed_time(e1) * 1e-3)
     return 2.0 * n ** 3 / best / 1e12
+
+
+def k1_grid(rt, torch, peak):
+    """AMEn local matvec (K1) on the scaled synthetic grid of SURVEY 8d, timed in this run (the second half of
+    BASELINE.json's metric: "AMEn matvec fp64 TFLOP/s"): CUDA events over back-to-back launches of
+    ttipm_block_matvec (equality KKT block structure, 6 terms), algorithmic flops of the reference's 3-GEMM order,
+    fraction of the cuBLAS DGEMM rate measured in this run.  Operands (<= 40 MB) are L2 resident by construction."""
+    from ttipm_b200 import kernels as K
+    rng = np.random.default_rng(0)
+    out = []
+    eq = lambda s: {(0, 0): s, (0, 1): s, (1, 2): 1, (2, 1): s, (2, 2): s}
+    shapes = [("maxcut_13 traced block (r = R = 55, s <= 5)", 55, {(0, 0): 2, (0, 1): 1, (1, 2): 1, (2, 1): 5, (2, 2): 5}),
+              ("r = R = 110, s = 5", 110, eq(5)), ("r = R = 128, s = 16", 128, eq(16)), ("r = R = 256, s = 16", 256, eq(16))]
+    for name, r, ranks in shapes:
+        A = {k: rt.to_device(rng.standard_normal((s, 4, 4, s))) for k, s in ranks.items()}
+        P = {k: rt.to_device(rng.standard_normal((r, s, r))) for k, s in ranks.items()}
+        x = rt.to_device(rng.standard_normal((r, 3, 4, r)))
+        tl = K.TermList()
+        flops = 0.0
+        for (i, j), s_ in ranks.items():
+            tl.add(P[i, j], A[i, j], P[i, j], j, i)
+            flops += term_flops(r, r, s_, s_)
+            if (i, j) == (0, 1):
+                tl.add(P[i, j].permute(2, 1, 0), A[i, j].permute(0, 2, 1, 3), P[i, j].permute(2, 1, 0), 0, 1)
+                flops += term_flops(r, r, s_, s_)
+        for _ in range(3):
+            K.block_matvec(tl, x, 3, (r, r), rt=rt)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 10
+        e0.record()
+        for _ in range(iters):
+            K.block_matvec(tl, x, 3, (r, r), rt=rt)
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3 / iters
+        out.append({"shape": name, "flops": flops, "us": sec * 1e6, "tflops": flops / sec / 1e12,
+                    "frac_of_dgemm": flops / sec / 1e12 / peak})
+    return out
 
 
 def main():
@@ -284,7 +334,7 @@ def main():
     from ttipm_b200 import get_runtime, kernels as K, tt as T
     from ttipm_b200.amen import DeviceBlockAmen, NativeBlockAmen
     rt = get_runtime()
-    systems = load_systems(args.workload)
+    systems = load_systems(args.workload, rank)
 
     # ---- problem set-up (not timed): upload operator blocks / rhs, retract warm starts like the reference ----
     def make(g):
@@ -465,6 +515,7 @@ def main():
             "roofline": roof,
             "kernels": kernels,
             "krylov": {"solves": lg_calls, "inner_iterations": lg_its},
+            "k1_grid": k1_grid(rt, torch, peak),
             "step_seconds": [float(t) for t in times],
             "warmup_step_seconds": [float(t) for t in warm_times],
             "final_local_residuals": res_check,

@@ -153,6 +153,8 @@ int ttipm_linalg_threads(int threads);
  * rows of R3 with a K x K accumulator): 1 (default) / 0 = single QR with the K x M accumulator.  Returns the previous
  * setting; a negative argument only queries. */
 int ttipm_linalg_tall_triple_qr(int on);
+/* tuning: smallest number of rows per Jacobi block (even; default 8); returns the previous value */
+int ttipm_linalg_block_rows(int nb);
 /* Rows of the Jacobi iteration whose norm is below factor * eps * ||R||_F are treated as numerically zero and left
  * alone (fewer sweeps on strongly graded unfoldings; singular values below that level then carry an absolute error of
  * that size, U stays orthonormal and U W = A).  Default 0 = off: every row pair is orthogonalised to relative accuracy,

@@ -857,6 +857,7 @@ static int g_tall_triple_qr = 1;
 static int g_coop_threads = 256;
 static int g_use_cluster = 1;
 static int g_wide_cta_min_dim = 96;
+static int g_min_block_rows = 8;
 
 struct LinPlan {
     LinParams p;
@@ -920,7 +921,7 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
     const long qr_doubles = p.oP + (panel_global ? 0 : (long)TT_QR_PB * p.ldp);
     // Jacobi block rows: 8, raised (even) until the block pairs of a round fit one thread-block cluster of 16 CTAs,
     // lowered until two blocks fit the shared memory of a CTA
-    int nb = 8;
+    int nb = g_min_block_rows;
     while ((K + nb - 1) / nb > 32 && (p.oRows + 2L * (nb + 2) * ldg) * 8 <= di.smem_optin - 1024) nb += 2;
     while (nb > 1 && (p.oRows + 2L * nb * ldg) * 8 > di.smem_optin - 1024) nb /= 2;
     p.nb = nb;
@@ -1013,6 +1014,12 @@ extern "C" int ttipm_linalg_threads(int threads) {
     const int old = g_coop_threads;
     if (threads == 256 || threads == 512) g_coop_threads = threads;
     g_wide_cta_min_dim = threads == 256 ? (1 << 30) : 96;           // 256: never widen (tuning runs)
+    return old;
+}
+
+extern "C" int ttipm_linalg_block_rows(int nb) {
+    const int old = g_min_block_rows;
+    if (nb >= 2) g_min_block_rows = nb & ~1;
     return old;
 }
 

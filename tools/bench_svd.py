@@ -70,8 +70,14 @@ def main():
     rng = np.random.default_rng(0)
     shapes = [(16, 12), (32, 24), (64, 48), (88, 66), (136, 81), (296, 102), (102, 296), (220, 165), (165, 220), (440, 330),
               (330, 440), (400, 156), (208, 96), (24, 440)]
-    if len(sys.argv) > 1:
-        shapes = [tuple(int(v) for v in s.split("x")) for s in sys.argv[1:]]
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    if "--single-qr" in sys.argv:
+        rt.lib.ttipm_linalg_tall_triple_qr(0)       # tall matrices: one QR instead of three before the Jacobi sweeps
+    for a in sys.argv[1:]:
+        if a.startswith("--nb="):
+            rt.lib.ttipm_linalg_block_rows(int(a[5:]))
+    if args:
+        shapes = [tuple(int(v) for v in s.split("x")) for s in args]
     out = []
     for (M, N) in shapes:
         for kind, a in (("graded18", graded(M, N, 18, rng)), ("plateau", plateau(M, N, rng))):
@@ -83,7 +89,7 @@ def main():
                 print(json.dumps(rec), flush=True)
                 out.append(rec)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "bench_svd.jsonl"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", "bench_svd_single.jsonl" if "--single-qr" in sys.argv else "bench_svd.jsonl"), "w") as f:
         for rec in out:
             f.write(json.dumps(rec) + "\n")
 

@@ -15,4 +15,11 @@ for d in src psd_system configs; do cp -r /root/reference/$d "$STAGE/$d"; done
 find "$STAGE" -name '*.so' -delete
 python tensor-train-interior-point-method_b200/build.py > /dev/null
 mkdir -p gpurun_out
-gpurun --timeout "$1" -- "export TTIPM_REF_TREE=\$PWD/$STAGE; $2" > "${3:-gpurun_out/last_e2e.log}" 2>&1
+for attempt in $(seq 1 20); do      # exit code 3 = no GPU slot free right now (nothing charged): retry
+  set +e
+  gpurun --timeout "$1" -- "export TTIPM_REF_TREE=\$PWD/$STAGE; $2" > "${3:-gpurun_out/last_e2e.log}" 2>&1
+  rc=$?
+  set -e
+  if [ $rc -ne 3 ]; then break; fi
+  sleep 90
+done
