@@ -242,6 +242,41 @@ int ttipm_amen_profile(ttipm_amen* h, double* out);
  * algorithmic flops; trace: 5 doubles (swp, k, res_old, res_new, r*R) per solve */
 int ttipm_amen_stats(ttipm_amen* h, double* stats, double* trace, int max_trace_rows);
 
+/* ---- device-resident tensor trains: the TT algebra of cy_src/tt_ops_cy.pyx behind handles ------------
+ * A ttipm_tt holds the cores of one train in HBM; operations run their whole per-core loop natively on `stream` and
+ * synchronise only for the singular values the reference's rank rule needs.  dims = 4 ints per core: r, n1, n2
+ * (0 for a 3-D core (r, n1, R)), R; host buffers hold the cores concatenated, row-major. */
+typedef struct ttipm_tt ttipm_tt;
+ttipm_tt* ttipm_tt_create(int d, void* stream);
+void ttipm_tt_destroy(ttipm_tt* h);
+int ttipm_tt_length(const ttipm_tt* h);
+int ttipm_tt_set_cores(ttipm_tt* h, const double* host, const int32_t* dims);   /* one H2D copy */
+int ttipm_tt_shapes(const ttipm_tt* h, int32_t* dims);
+int ttipm_tt_get_cores(ttipm_tt* h, double* host);                              /* one D2H copy */
+ttipm_tt* ttipm_tt_clone(const ttipm_tt* src);                                   /* shares the device buffers */
+/* tt_scale multiplies ONE core (cy_src/tt_ops_cy.pyx:96-114; the host draws the index and rounds alpha to float32) */
+int ttipm_tt_scale_core(ttipm_tt* h, int k, double alpha);
+/* tt_rl_orthogonalise (cy_src/tt_ops_cy.pyx:132-159), in place */
+int ttipm_tt_rl_orthogonalise(ttipm_tt* h);
+/* tt_rank_reduce (cy_src/tt_ops_cy.pyx:180-226) with the per-bond tolerance eps (the caller applies eps / sqrt(d - 1));
+ * collect != 0: the tail-energy rule of tt_psd_rank_reduce / tt_mask_rank_reduce (:283-318), *dropped = discarded energy */
+int ttipm_tt_round(ttipm_tt* h, double eps, int collect, double* dropped);
+/* tt_add (cy_src/tt_ops_cy.pyx:244-258); NULL on failure */
+ttipm_tt* ttipm_tt_add(const ttipm_tt* a, const ttipm_tt* b);
+/* tt_inner_prod (cy_src/tt_ops_cy.pyx:506-520) */
+int ttipm_tt_inner(ttipm_tt* a, const ttipm_tt* b, double* out);
+/* zip-up products with swap_cores (cy_src/tt_ops_cy.pyx:393-502): kind 0 tt_fast_matrix_vec_mul(A, B),
+ * 1 tt_fast_mat_mat_mul(A, B), 2 tt_fast_hadamard(A, B); eps as passed to the reference function; NULL on failure */
+ttipm_tt* ttipm_tt_zipup(int kind, const ttipm_tt* A, const ttipm_tt* B, double eps);
+/* tt_reshape without core merging (src/tt_ops.py:330-333): same buffers, modes (n1, n2) (n2 = 0: a single mode) */
+ttipm_tt* ttipm_tt_reshape(const ttipm_tt* src, int n1, int n2);
+/* tt_transpose of a train of 4-D cores (cy_src/tt_ops_cy.pyx:57-78), materialised */
+ttipm_tt* ttipm_tt_transpose(const ttipm_tt* src);
+/* per-core embeddings: kind 0 I (x) M (tt_IkronM), 1 M (x) I (tt_MkronI), 2 diagonal (tt_diag / tt_diag_op before
+ * rounding) -- src/tt_ops.py:312-316, :360-375 */
+ttipm_tt* ttipm_tt_embed(const ttipm_tt* src, int kind);
+int ttipm_tt_counters(const ttipm_tt* h, int64_t* launches, int64_t* syncs);
+
 /* ---- step-size eigen sweeps: local problems of tt_max_generalised_eigen / tt_min_eig ---------------
  * One- or two-site projection of a TT matrix onto the current interfaces,
  *   'lsr,smnk,kptS,LSR->lmpLrntR' (reference src/tt_als.py:952-959, :1305) or, with A2 == NULL,

@@ -89,6 +89,23 @@ SIGNATURES = {
     "ttipm_linalg_block_rows": (C.c_int, [C.c_int]),
     "ttipm_linalg_threads": (C.c_int, [C.c_int]),
     "ttipm_linalg_use_cluster": (C.c_int, [C.c_int]),
+    "ttipm_tt_create": (C.c_void_p, [C.c_int, C.c_void_p]),
+    "ttipm_tt_destroy": (None, [C.c_void_p]),
+    "ttipm_tt_length": (C.c_int, [C.c_void_p]),
+    "ttipm_tt_set_cores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ttipm_tt_shapes": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ttipm_tt_get_cores": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ttipm_tt_clone": (C.c_void_p, [C.c_void_p]),
+    "ttipm_tt_scale_core": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "ttipm_tt_rl_orthogonalise": (C.c_int, [C.c_void_p]),
+    "ttipm_tt_round": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_double)]),
+    "ttipm_tt_add": (C.c_void_p, [C.c_void_p, C.c_void_p]),
+    "ttipm_tt_inner": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
+    "ttipm_tt_zipup": (C.c_void_p, [C.c_int, C.c_void_p, C.c_void_p, C.c_double]),
+    "ttipm_tt_reshape": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
+    "ttipm_tt_transpose": (C.c_void_p, [C.c_void_p]),
+    "ttipm_tt_embed": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "ttipm_tt_counters": (C.c_int, [C.c_void_p, C.POINTER(i64), C.POINTER(i64)]),
     "ttipm_eig_assemble": (C.c_int, [C.POINTER(EigOp), C.c_int, C.c_void_p, C.c_void_p]),
     "ttipm_eig_workspace": (i64, [C.c_int, C.c_int]),
     "ttipm_eig_lanczos": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_int,

@@ -10,17 +10,24 @@ Functions ending in `_dev` take and return lists of device tensors, so composite
 their intermediates in HBM; the NumPy-boundary wrappers upload once and download once.
 """
 import math
+from ctypes import c_double as C_double
 
 import numpy as np
 
 from . import kernels as K
+from .devtt import Handle, TTList, as_handle, shapes_of
 from .runtime import get_runtime
+
+
+def _native(ptr, rt):
+    """TTList around a freshly created ttipm_tt handle (raises on NULL)."""
+    return TTList(Handle(ptr, rt))
 
 
 # ---- pure bookkeeping (no arithmetic): kept on the host exactly as in the reference ---------------
 def tt_ranks(tt):
-    """cy_src/tt_ops_cy.pyx:82-92."""
-    return [c.shape[0] for c in tt[1:]]
+    """cy_src/tt_ops_cy.pyx:82-92 (shapes only: a device-resident train is not downloaded)."""
+    return [sh[0] for sh in shapes_of(tt)[1:]]
 
 
 def tt_identity(dim):
@@ -43,6 +50,10 @@ def tt_one_matrix(dim):
 
 def tt_transpose(tt):
     """cy_src/tt_ops_cy.pyx:57-78 (views; axes 1,2 swapped from the first 4-D core onward)."""
+    if isinstance(tt, TTList) and all(len(sh) == 4 for sh in tt.shapes()):
+        h = tt.handle()
+        if h is not None:
+            return _native(h.rt.lib.ttipm_tt_transpose(h.ptr), h.rt)
     split = int(np.argmax([np.ndim(c) for c in tt]))
     return list(tt[:split]) + [np.swapaxes(c, 1, 2) for c in tt[split:]]
 
@@ -62,7 +73,13 @@ def tt_merge_cores(tt):
 
 def tt_reshape(tt, shape):
     """src/tt_ops.py:330-333."""
-    if np.prod(shape) > np.prod(tt[0].shape[1:-1]):
+    shapes = shapes_of(tt)
+    merge = np.prod(shape) > np.prod(shapes[0][1:-1])
+    if isinstance(tt, TTList) and not merge and len(shape) in (1, 2):
+        h = tt.handle()
+        if h is not None:
+            return _native(h.rt.lib.ttipm_tt_reshape(h.ptr, int(shape[0]), int(shape[1]) if len(shape) == 2 else 0), h.rt)
+    if merge:
         tt = tt_merge_cores(tt)
     return [c.reshape(c.shape[0], *shape, c.shape[-1]) for c in tt]
 
@@ -71,12 +88,11 @@ def tt_scale(alpha, tt):
     """cy_src/tt_ops_cy.pyx:96-114: the C signature rounds alpha to float32 and ONE core, drawn with
     np.random.randint (advancing the global RNG), is scaled; all other cores are shared."""
     idx = np.random.randint(0, len(tt))
-    out = list(tt)
     a32 = float(np.float32(alpha))
     rt = get_runtime()
-    core = rt.to_device(tt[idx])
-    out[idx] = rt.to_host(K.ewise(core, a32, rt=rt)).reshape(tt[idx].shape)
-    return out
+    h = as_handle(tt, rt).clone()
+    rt.check(rt.lib.ttipm_tt_scale_core(h.ptr, int(idx), a32), "ttipm_tt_scale_core")
+    return TTList(h)
 
 
 def prune_singular_vals(s, eps):
@@ -241,14 +257,41 @@ def tt_fast_hadamard_dev(a, b, eps, rt):
 
 
 # ---- NumPy-boundary API (reference signatures) -----------------------------------------------------
+def _assign(train_tt, h):
+    """The reference's in-place semantics: the caller's list object now holds the train behind `h`."""
+    h._shapes = None
+    if isinstance(train_tt, TTList):
+        train_tt.rebind(h)
+    else:
+        train_tt[:] = h.to_numpy()
+    return train_tt
+
+
+def _own_handle(train_tt, rt):
+    """A handle the call may modify in place: the train's own handle, or a fresh upload."""
+    h = as_handle(train_tt, rt)
+    return h if not isinstance(train_tt, TTList) or not train_tt._live else h.clone()
+
+
 def tt_rl_orthogonalise(train_tt):
     """cy_src/tt_ops_cy.pyx:132-159; mutates and returns the input list."""
     if len(train_tt) == 1:
         return train_tt
     rt = get_runtime()
-    dev = tt_rl_orthogonalise_dev(_up(train_tt, rt), rt)
-    train_tt[:] = _down(dev, rt)
-    return train_tt
+    h = _own_handle(train_tt, rt)
+    rt.check(rt.lib.ttipm_tt_rl_orthogonalise(h.ptr), "ttipm_tt_rl_orthogonalise")
+    return _assign(train_tt, h)
+
+
+def _round_native(h, eps, rt, collect=False):
+    """rl-orthogonalise + truncation sweep on a handle with the per-train eps of the reference (eps / sqrt(d - 1) per
+    bond); returns the discarded energy of the collecting variant."""
+    d = len(h.shapes())
+    dropped = C_double(0.0)
+    rt.check(rt.lib.ttipm_tt_round(h.ptr, float(eps / np.sqrt(d - 1)) if d > 1 else float(eps), int(collect), dropped),
+             "ttipm_tt_round")
+    h._shapes = None
+    return float(dropped.value)
 
 
 def tt_rank_reduce(train_tt, eps=1e-18):
@@ -256,17 +299,16 @@ def tt_rank_reduce(train_tt, eps=1e-18):
     if _all_rank_one(train_tt):
         return train_tt
     rt = get_runtime()
-    eps = eps / np.sqrt(len(train_tt) - 1)
-    dev = tt_rl_orthogonalise_dev(_up(train_tt, rt), rt)
-    _round_sweep_dev(dev, eps, rt)
-    train_tt[:] = _down(dev, rt)
-    return train_tt
+    h = _own_handle(train_tt, rt)
+    _round_native(h, eps, rt)
+    return _assign(train_tt, h)
 
 
 def tt_add(train_1_tt, train_2_tt):
     """cy_src/tt_ops_cy.pyx:244-258."""
     rt = get_runtime()
-    return _down(tt_add_dev(_up(train_1_tt, rt), _up(train_2_tt, rt), rt), rt)
+    a, b = as_handle(train_1_tt, rt), as_handle(train_2_tt, rt)
+    return _native(rt.lib.ttipm_tt_add(a.ptr, b.ptr), rt)
 
 
 def tt_sub(train_1_tt, train_2_tt):
@@ -280,12 +322,12 @@ def _psd_like(train_tt, extra_fn, eps):
     if _all_rank_one(train_tt):
         return train_tt
     rt = get_runtime()
-    eps = eps / np.sqrt(d - 1)
-    dev = tt_rl_orthogonalise_dev(_up(train_tt, rt), rt)
-    dropped = _round_sweep_dev(dev, eps, rt, collect=True)
-    train_tt[:] = _down(dev, rt)           # the reference mutates its input before adding the correction
+    h = _own_handle(train_tt, rt)
+    dropped = _round_native(h, eps, rt, collect=True)
+    _assign(train_tt, h)                   # the reference mutates its input before adding the correction
     factor = pow(dropped, 1.0 / (2 * d))
-    return _down(tt_add_dev(dev, _up(extra_fn(factor), rt), rt), rt)
+    extra = Handle.from_numpy(extra_fn(factor), rt)
+    return _native(rt.lib.ttipm_tt_add(h.ptr, extra.ptr), rt)
 
 
 def tt_psd_rank_reduce(train_tt, eps=1e-18):
@@ -302,7 +344,10 @@ def tt_mask_rank_reduce(train_tt, mask_tt, eps=1e-18):
 def tt_inner_prod(train_1_tt, train_2_tt):
     """cy_src/tt_ops_cy.pyx:506-520."""
     rt = get_runtime()
-    return float(rt.to_host(tt_inner_prod_dev(_up(train_1_tt, rt), _up(train_2_tt, rt), rt))[0, 0])
+    a, b = as_handle(train_1_tt, rt), as_handle(train_2_tt, rt)
+    out = C_double(0.0)
+    rt.check(rt.lib.ttipm_tt_inner(a.ptr, b.ptr, out), "ttipm_tt_inner")
+    return float(out.value)
 
 
 def tt_norm(train_tt):
@@ -320,19 +365,22 @@ def tt_normalise(train_tt, radius=1):
 def tt_fast_matrix_vec_mul(matrix_tt, vec_tt, eps=1e-18):
     """cy_src/tt_ops_cy.pyx:430-447."""
     rt = get_runtime()
-    return _down(tt_fast_matrix_vec_mul_dev(_up(matrix_tt, rt), _up(vec_tt, rt), eps, rt), rt)
+    A, B = as_handle(matrix_tt, rt), as_handle(vec_tt, rt)
+    return _native(rt.lib.ttipm_tt_zipup(0, A.ptr, B.ptr, float(eps)), rt)
 
 
 def tt_fast_mat_mat_mul(matrix_tt_1, matrix_tt_2, eps=1e-18):
     """cy_src/tt_ops_cy.pyx:451-464."""
     rt = get_runtime()
-    return _down(tt_fast_mat_mat_mul_dev(_up(matrix_tt_1, rt), _up(matrix_tt_2, rt), eps, rt), rt)
+    A, B = as_handle(matrix_tt_1, rt), as_handle(matrix_tt_2, rt)
+    return _native(rt.lib.ttipm_tt_zipup(1, A.ptr, B.ptr, float(eps)), rt)
 
 
 def tt_fast_hadamard(train_tt_1, train_tt_2, eps=1e-18):
     """cy_src/tt_ops_cy.pyx:468-502."""
     rt = get_runtime()
-    return _down(tt_fast_hadamard_dev(_up(train_tt_1, rt), _up(train_tt_2, rt), eps, rt), rt)
+    A, B = as_handle(train_tt_1, rt), as_handle(train_tt_2, rt)
+    return _native(rt.lib.ttipm_tt_zipup(2, A.ptr, B.ptr, float(eps)), rt)
 
 
 def tt_random_gaussian(target_ranks, shape=(2,)):
@@ -347,9 +395,9 @@ def tt_mat_vec_mul(mat, vec, op_tol, eps, verbose=False):
     ALS fit of the product (als_product.tt_approx_mat_vec_mul, which draws from the global NumPy RNG like the
     reference's)."""
     if np.max(np.array(tt_ranks(mat)) * np.array(tt_ranks(vec))) <= 80:
-        rt = get_runtime()
-        dev = tt_fast_matrix_vec_mul_dev(_up(mat, rt), _up(vec, rt), eps, rt)
-        return _round_dev_to_host(dev, op_tol, rt)
+        out = tt_fast_matrix_vec_mul(mat, vec, eps)
+        _round_native(out._h, op_tol, get_runtime())
+        return out
     from .als_product import tt_approx_mat_vec_mul
     return tt_approx_mat_vec_mul(mat, vec, tol=op_tol, verbose=verbose)
 
@@ -357,9 +405,9 @@ def tt_mat_vec_mul(mat, vec, op_tol, eps, verbose=False):
 def tt_mat_mat_mul(mat1, mat2, op_tol, eps, verbose=False):
     """src/tt_als.py:1631-1634: exact zip-up product rounded to op_tol up to a rank product of 40, ALS fit above."""
     if np.max(np.array(tt_ranks(mat1)) * np.array(tt_ranks(mat2))) <= 40:
-        rt = get_runtime()
-        dev = tt_fast_mat_mat_mul_dev(_up(mat1, rt), _up(mat2, rt), eps, rt)
-        return _round_dev_to_host(dev, op_tol, rt)
+        out = tt_fast_mat_mat_mul(mat1, mat2, eps)
+        _round_native(out._h, op_tol, get_runtime())
+        return out
     from .als_product import tt_approx_mat_mat_mul
     return tt_approx_mat_mat_mul(mat1, mat2, tol=op_tol, verbose=verbose)
 
@@ -373,32 +421,36 @@ def _round_dev_to_host(dev, eps, rt):
     return _down(dev, rt)
 
 
+def _embed(tt, kind):
+    rt = get_runtime()
+    h = as_handle(tt, rt)                  # keep the (possibly temporary) handle alive across the call
+    return _native(rt.lib.ttipm_tt_embed(h.ptr, kind), rt)
+
+
 def tt_IkronM(matrix_tt):
     """src/tt_ops.py:360-363: I (x) M per core."""
-    rt = get_runtime()
-    return [rt.to_host(K.embed(rt.to_device(c), "IkronM", rt=rt)) for c in matrix_tt]
+    return _embed(matrix_tt, 0)
 
 
 def tt_MkronI(matrix_tt):
     """src/tt_ops.py:365-368."""
-    rt = get_runtime()
-    return [rt.to_host(K.embed(rt.to_device(c), "MkronI", rt=rt)) for c in matrix_tt]
+    return _embed(matrix_tt, 1)
 
 
-def _diag_embed_tt(cores3, eps):
-    rt = get_runtime()
-    dev = [K.embed(rt.to_device(c), "diag", rt=rt) for c in cores3]
-    return _round_dev_to_host(dev, eps, rt)
+def _diag_embed_tt(tt, eps):
+    out = _embed(tt, 2)
+    _round_native(out._h, eps, get_runtime())
+    return out
 
 
 def tt_diag(vec_tt, eps=1e-18):
     """src/tt_ops.py:312-316."""
-    return _diag_embed_tt([np.ascontiguousarray(c) for c in vec_tt], eps)
+    return _diag_embed_tt(vec_tt, eps)
 
 
 def tt_diag_op(matrix_tt, eps=1e-18):
     """src/tt_ops.py:371-375."""
-    return _diag_embed_tt([np.ascontiguousarray(c).reshape(c.shape[0], -1, c.shape[-1]) for c in matrix_tt], eps)
+    return _diag_embed_tt(matrix_tt, eps)
 
 
 def tt_diagonal(matrix_tt):
@@ -408,7 +460,7 @@ def tt_diagonal(matrix_tt):
 
 def tt_entrywise_sum(train_tt):
     """src/tt_ops.py:342-352: inner product with the all-ones train."""
-    ones = [np.ones((1, *c.shape[1:-1], 1)) for c in train_tt]
+    ones = [np.ones((1, *sh[1:-1], 1)) for sh in shapes_of(train_tt)]
     return tt_inner_prod(train_tt, ones)
 
 
