@@ -878,7 +878,10 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
     p.floor_factor = g_floor_factor;
     p.M1 = wide ? N : M;
     p.N1 = wide ? M : N;
-    p.triple = (mode == 0 && !wide && g_tall_triple_qr) ? 1 : 0;
+    // three QR factorisations pay off through the sweep count of graded unfoldings; below ~16 columns the sweeps are few
+    // either way and the two extra factorisations are a third of the kernel (measured on B200: 8 x 6 .. 216 x 6 unfoldings
+    // 58 -> 40 us with the single-QR form)
+    p.triple = (mode == 0 && !wide && g_tall_triple_qr && K > 16) ? 1 : 0;
     p.Mj = (wide || p.triple) ? (int)K : M;
     p.ld1 = (int)even_up(p.M1);
     p.ldk = (int)even_up(K);

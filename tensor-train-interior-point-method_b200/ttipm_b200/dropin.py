@@ -16,7 +16,10 @@ from . import lgmres, tt, tt_als
 TT_OPS = ["tt_add", "tt_sub", "tt_scale", "tt_inner_prod", "tt_norm", "tt_normalise", "tt_rank_reduce",
           "tt_psd_rank_reduce", "tt_mask_rank_reduce", "tt_rl_orthogonalise", "tt_fast_matrix_vec_mul",
           "tt_fast_mat_mat_mul", "tt_fast_hadamard", "tt_IkronM", "tt_MkronI", "tt_diag", "tt_diag_op",
-          "tt_entrywise_sum", "tt_rank_retraction", "tt_rl_orthogonalise_py", "tt_sum", "prune_singular_vals"]
+          "tt_entrywise_sum", "tt_rank_retraction", "tt_rl_orthogonalise_py", "tt_sum", "prune_singular_vals",
+          # shape / view helpers: the reference's Cython versions are typed `list` and reject the lazy TTList the
+          # functions above return; these also keep device-resident trains on the device (tt_ranks, tt_reshape, tt_transpose)
+          "tt_ranks", "tt_reshape", "tt_transpose", "tt_swap_all", "tt_diagonal", "tt_random_gaussian", "tt_merge_cores"]
 TT_ALS = ["tt_restarted_block_amen", "tt_block_amen", "tt_mat_vec_mul", "tt_mat_mat_mul", "tt_approx_mat_vec_mul",
           "tt_approx_mat_mat_mul", "tt_max_generalised_eigen", "tt_min_eig", "TTBlockMatrix",
           "TTBlockVector", "compute_phi_bck_A", "compute_phi_fwd_A", "compute_phi_bck_rhs", "compute_phi_fwd_rhs"]
