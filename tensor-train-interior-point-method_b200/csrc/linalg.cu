@@ -880,8 +880,8 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
     p.N1 = wide ? M : N;
     // three QR factorisations pay off through the sweep count of graded unfoldings; below ~16 columns the sweeps are few
     // either way and the two extra factorisations are a third of the kernel (measured on B200: 8 x 6 .. 216 x 6 unfoldings
-    // 58 -> 40 us with the single-QR form)
-    p.triple = (mode == 0 && !wide && g_tall_triple_qr && K > 16) ? 1 : 0;
+    // 58 -> 40 us, 32 x 24 and 68 x 24 0.25-0.29 -> 0.21-0.22 ms with the single-QR form; equal at 52 x 39)
+    p.triple = (mode == 0 && !wide && g_tall_triple_qr && K > 32) ? 1 : 0;
     p.Mj = (wide || p.triple) ? (int)K : M;
     p.ld1 = (int)even_up(p.M1);
     p.ldk = (int)even_up(K);

@@ -20,7 +20,9 @@ import kernel_cases as KC
 import rt_util
 import tt_oracle as O
 
-WITH_REF_OUTPUT = [f for f in G.amen_files("amen_*.npz") if "out/x/0" in np.load(f).files]
+# the extra maxcut_13 seeds are bench inputs only (see tests/test_oracle_vs_golden.py)
+WITH_REF_OUTPUT = [f for f in G.amen_files("amen_*.npz") if "out/x/0" in np.load(f).files and
+                   not any(f"maxcut_13_r2_s{s}_" in f for s in (45, 23, 53, 12))]
 
 
 def _containers(g):
