@@ -21,8 +21,12 @@ TT_OPS = ["tt_add", "tt_sub", "tt_scale", "tt_inner_prod", "tt_norm", "tt_normal
           # functions above return; these also keep device-resident trains on the device (tt_ranks, tt_reshape, tt_transpose)
           "tt_ranks", "tt_reshape", "tt_transpose", "tt_swap_all", "tt_diagonal", "tt_random_gaussian", "tt_merge_cores"]
 TT_ALS = ["tt_restarted_block_amen", "tt_block_amen", "tt_mat_vec_mul", "tt_mat_mat_mul", "tt_approx_mat_vec_mul",
-          "tt_approx_mat_mat_mul", "tt_max_generalised_eigen", "tt_min_eig", "TTBlockMatrix",
-          "TTBlockVector", "compute_phi_bck_A", "compute_phi_fwd_A", "compute_phi_bck_rhs", "compute_phi_fwd_rhs"]
+          "tt_approx_mat_mat_mul", "tt_max_generalised_eigen", "tt_min_eig",
+          "compute_phi_bck_A", "compute_phi_fwd_A", "compute_phi_bck_rhs", "compute_phi_fwd_rhs"]
+# The containers TTBlockMatrix / TTBlockVector are NOT rebound: in drop-in mode the reference's own classes stay (the IPM
+# driver reaches into their _data / _aliases / _transposes dicts, src/tt_ipm.py:534-556); the device sweep only reads
+# those three dicts, and the containers' own TT arithmetic (block_product, __sub__, norm) calls module-level functions
+# that ARE rebound.  ttipm_b200.tt_als carries equivalent classes for the stand-alone layout (Option B).
 LGMRES = ["MatVecWrapper", "IneqMatVecWrapper"]
 
 

@@ -97,7 +97,33 @@ class TTBlockVectorView:
         return rt.to_host(out)
 
 
-class TTBlockMatrix:
+class _BlockKeys:
+    """Key sets of a block operator: stored blocks plus the positions their (transpose) aliases fill
+    (reference src/tt_als.py:113-129, :176-188).  Shared by the matrix and its per-core view."""
+
+    def __iter__(self):
+        return iter(self._data)
+
+    def keys(self):
+        return self._data.keys()
+
+    def _with(self, *alias_maps):
+        out = set(self._data.keys())
+        for m in alias_maps:
+            out |= set(m.values())
+        return out
+
+    def tkeys(self):
+        return self._with(self._transposes)
+
+    def akeys(self):
+        return self._with(self._aliases)
+
+    def all_keys(self):
+        return self._with(self._aliases, self._transposes)
+
+
+class TTBlockMatrix(_BlockKeys):
     def __init__(self):
         self._data = {}
         self._aliases = {}
@@ -120,21 +146,6 @@ class TTBlockMatrix:
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self._data})"
-
-    def __iter__(self):
-        return iter(self._data)
-
-    def keys(self):
-        return self._data.keys()
-
-    def tkeys(self):
-        return self._data.keys() | self._transposes.values()
-
-    def akeys(self):
-        return self._data.keys() | self._aliases.values()
-
-    def all_keys(self):
-        return self._data.keys() | self._aliases.values() | self._transposes.values()
 
     def block_product(self, x_cores, op_tol, eps=1e-12):
         """A x in TT format, block row by block row (reference src/tt_als.py:132-155)."""
@@ -164,7 +175,7 @@ class TTBlockMatrix:
         return sub
 
 
-class TTBlockMatrixView:
+class TTBlockMatrixView(_BlockKeys):
     """Per-core view; the four local products run on the device (reference src/tt_als.py:190-238)."""
 
     def __init__(self, data, aliases, transposes, list_index):
@@ -183,23 +194,8 @@ class TTBlockMatrixView:
             if len(values) > self._idx:
                 yield coord, values[self._idx]
 
-    def __iter__(self):
-        return iter(self._data)
-
     def __repr__(self):
         return f"IndexView({self._idx})"
-
-    def keys(self):
-        return self._data.keys()
-
-    def tkeys(self):
-        return self._data.keys() | self._transposes.values()
-
-    def akeys(self):
-        return self._data.keys() | self._aliases.values()
-
-    def all_keys(self):
-        return self._data.keys() | self._aliases.values() | self._transposes.values()
 
     def _product(self, left, right, x_core, shape, left_is_z, right_is_z):
         rt = get_runtime()
