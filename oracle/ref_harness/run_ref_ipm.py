@@ -44,7 +44,8 @@ def run(problem, dim, rank, seed, verbose=True):
     t0 = time.time()
     X, Y, Tt, Z, info = ref.tt_ipm.tt_ipm(
         lag_maps, obj_tt, L_op_tt, bias_tt, ineq_mask=ineq_mask,
-        max_iter=cfg["max_iter"], verbose=verbose, gap_tol=float(cfg["gap_tol"]),
+        max_iter=int(os.environ.get("TTIPM_MAX_ITER", cfg["max_iter"])),       # env: profiling runs stop early
+        verbose=verbose, gap_tol=float(cfg["gap_tol"]),
         op_tol=float(cfg["op_tol"]), warm_up=cfg["warm_up"], abs_tol=float(cfg["abs_tol"]),
         aho_direction=False, mals_restarts=cfg["mals_restarts"],
         max_refinement=cfg["max_refinement"], lambdaStar=float(cfg.get("lambdaStar", 1)),

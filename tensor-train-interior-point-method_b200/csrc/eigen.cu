@@ -28,42 +28,31 @@ namespace ttipm {
 
 // ------------------------------------------------------------------------------------------------------------------
 // dense symmetric assembly
+//   M[(l,m,p,L), (r,n,t,R)] = sum_S W[l,r,m,n,p,t,S] P2[L,S,R],   W = (P1 . A1) . A2  built by two GEMMs on the host side
+// (the contraction order opt_einsum picks for the reference's 'lsr,smnk,kptS,LSR->lmpLrntR': the operator ranks s, k
+// only enter the two small GEMMs, never the m^2 outputs -- the step direction of a large Newton solve has TT ranks
+// of ~100, where the naive s k S terms per output would be 10^6).
 // ------------------------------------------------------------------------------------------------------------------
 struct EigAsmParams {
-    const double* P1;   // (l, s, l) through p1s
-    const double* A1;   // (s, n1, n1, k) through a1s
-    const double* A2;   // (k, n2, n2, S) through a2s, or nullptr (one-site: k == S, n2 == 1)
+    const double* W;    // (l, l, n1, n1, n2, n2, S) contiguous
     const double* P2;   // (L, S, L) through p2s
-    int p1s[3], a1s[4], a2s[4], p2s[3];
-    int l, s, k, S, L, n1, n2;
+    int p2s[3];
+    int l, S, L, n1, n2;
     int symmetrise;
     double* out;        // (l n1 n2 L)^2 row-major
 };
 
 TT_DEV double eig_asm_entry(const EigAsmParams& p, int lam, int m1, int m2, int Lam, int rho, int q1, int q2, int Rho) {
-    double acc = 0.0;
-    for (int sg = 0; sg < p.s; ++sg) {
-        const double p1 = p.P1[lam * p.p1s[0] + sg * p.p1s[1] + rho * p.p1s[2]];
-        if (p1 == 0.0) continue;
-        double inner = 0.0;
-        if (p.A2) {
-            for (int kk = 0; kk < p.k; ++kk) {
-                const double a1 = p.A1[sg * p.a1s[0] + m1 * p.a1s[1] + q1 * p.a1s[2] + kk * p.a1s[3]];
-                if (a1 == 0.0) continue;
-                double t = 0.0;
-                for (int sp = 0; sp < p.S; ++sp)
-                    t += p.A2[kk * p.a2s[0] + m2 * p.a2s[1] + q2 * p.a2s[2] + sp * p.a2s[3]] *
-                         p.P2[Lam * p.p2s[0] + sp * p.p2s[1] + Rho * p.p2s[2]];
-                inner += a1 * t;
-            }
-        } else {
-            for (int sp = 0; sp < p.S; ++sp)
-                inner += p.A1[sg * p.a1s[0] + m1 * p.a1s[1] + q1 * p.a1s[2] + sp * p.a1s[3]] *
-                         p.P2[Lam * p.p2s[0] + sp * p.p2s[1] + Rho * p.p2s[2]];
-        }
-        acc += p1 * inner;
+    const double* w = p.W + ((((((long)lam * p.l + rho) * p.n1 + m1) * p.n1 + q1) * p.n2 + m2) * p.n2 + q2) * p.S;
+    const double* p2 = p.P2 + (long)Lam * p.p2s[0] + (long)Rho * p.p2s[2];
+    double acc0 = 0.0, acc1 = 0.0;
+    int sp = 0;
+    for (; sp + 1 < p.S; sp += 2) {
+        acc0 += w[sp] * p2[(long)sp * p.p2s[1]];
+        acc1 += w[sp + 1] * p2[(long)(sp + 1) * p.p2s[1]];
     }
-    return acc;
+    if (sp < p.S) acc0 += w[sp] * p2[(long)sp * p.p2s[1]];
+    return acc0 + acc1;
 }
 
 TT_GLOBAL void k_eig_assemble(const EigAsmParams p) {
@@ -680,30 +669,71 @@ extern "C" int ttipm_eig_force_cluster(int ctas) {
     return 0;
 }
 
+static bool eig_contig(const int64_t* st, const int* dims, int nd) {
+    long acc = 1;
+    for (int i = nd - 1; i >= 0; --i) {
+        if (dims[i] != 1 && st[i] != acc) return false;
+        acc *= dims[i];
+    }
+    return true;
+}
+
 extern "C" int ttipm_eig_assemble(const ttipm_eig_op* op, int symmetrise, double* out, void* stream) {
-    EigAsmParams p;
-    p.P1 = op->P1; p.A1 = op->A1; p.A2 = op->A2; p.P2 = op->P2;
-    for (int i = 0; i < 3; ++i) {
-        if (!fits_int(op->p1_strides[i]) || !fits_int(op->p2_strides[i])) return fail(1, "eig_assemble: stride overflow");
-        p.p1s[i] = (int)op->p1_strides[i];
-        p.p2s[i] = (int)op->p2_strides[i];
-    }
-    for (int i = 0; i < 4; ++i) {
-        if (!fits_int(op->a1_strides[i]) || !fits_int(op->a2_strides[i])) return fail(1, "eig_assemble: stride overflow");
-        p.a1s[i] = (int)op->a1_strides[i];
-        p.a2s[i] = (int)op->a2_strides[i];
-    }
-    p.l = op->l; p.s = op->s; p.k = op->k; p.S = op->S; p.L = op->L; p.n1 = op->n1; p.n2 = op->A2 ? op->n2 : 1;
-    if (p.l < 1 || p.L < 1 || p.n1 < 1 || p.n2 < 1 || p.s < 1 || p.S < 1) return fail(1, "eig_assemble: bad dims");
-    const long m = (long)p.l * p.n1 * p.n2 * p.L;
+    tt_stream_t st = (tt_stream_t)stream;
+    const int l = op->l, s = op->s, L = op->L, n1 = op->n1;
+    const bool two = op->A2 != nullptr;
+    const int k = op->k, S = two ? op->S : op->k, n2 = two ? op->n2 : 1;
+    if (l < 1 || L < 1 || n1 < 1 || n2 < 1 || s < 1 || S < 1 || k < 1) return fail(1, "eig_assemble: bad dims");
+    const long m = (long)l * n1 * n2 * L;
     if (m * m > (1L << 31)) return fail(1, "eig_assemble: m=%ld too large for a dense projection", m);
-    p.symmetrise = symmetrise;
-    p.out = out;
-    const int bt = block_threads();
-    long blocks = (m * m + bt - 1) / bt;
-    const long cap = (long)dev_info().sms * 8;
-    if (blocks > cap) blocks = cap;
-    return launch_kernel("k_eig_assemble", k_eig_assemble, dim3((unsigned)blocks), dim3(bt), 0, (tt_stream_t)stream, false, p);
+    const int d1[3] = {l, s, l}, dA1[4] = {s, n1, n1, k}, dA2[4] = {k, n2, n2, S};
+    if (!eig_contig(op->p1_strides, d1, 3) || !eig_contig(op->a1_strides, dA1, 4) ||
+        (two && !eig_contig(op->a2_strides, dA2, 4)))
+        return fail(1, "eig_assemble: P1, A1, A2 must be contiguous");
+    for (int i = 0; i < 3; ++i)
+        if (!fits_int(op->p2_strides[i])) return fail(1, "eig_assemble: stride overflow");
+    // W = ((l r) x s) . (s x n1 n1 k) -> ((l r n1 n1) x k) . (k x n2 n2 S)
+    const long nP = (long)l * l * s, nT1 = (long)l * l * n1 * n1 * k, nT2 = two ? (long)l * l * n1 * n1 * n2 * n2 * S : 0;
+    double* scratch = nullptr;
+#ifdef TTIPM_EMU
+    scratch = (double*)malloc(sizeof(double) * (size_t)(nP + nT1 + nT2 + 8));
+#else
+    if (cudaMallocAsync((void**)&scratch, sizeof(double) * (size_t)(nP + nT1 + nT2 + 8), st) != cudaSuccess)
+        return fail(91, "eig_assemble: device allocation failed");
+#endif
+    double* P1p = scratch;
+    double* T1 = P1p + nP;
+    double* T2 = T1 + nT1;
+    int rc = 0;
+    {
+        int32_t dims[4] = {1, l, s, l}, perm[4] = {0, 1, 3, 2};
+        rc = ttipm_permute4(op->P1, dims, perm, P1p, nullptr, 0, 1, stream);                  // (l, s, r) -> (l, r, s)
+    }
+    const long c1 = (long)n1 * n1 * k;
+    if (!rc) rc = ttipm_gemm((int)((long)l * l), (int)c1, s, 1.0, P1p, s, 1, 0, op->A1, c1, 1, 0, 0.0, T1, c1, 1, 0, 1, stream);
+    const double* W = T1;
+    if (!rc && two) {
+        const long c2 = (long)n2 * n2 * S;
+        rc = ttipm_gemm((int)((long)l * l * n1 * n1), (int)c2, k, 1.0, T1, k, 1, 0, op->A2, c2, 1, 0, 0.0, T2, c2, 1, 0, 1, stream);
+        W = T2;
+    }
+    if (!rc) {
+        EigAsmParams p;
+        p.W = W; p.P2 = op->P2;
+        for (int i = 0; i < 3; ++i) p.p2s[i] = (int)op->p2_strides[i];
+        p.l = l; p.S = S; p.L = L; p.n1 = n1; p.n2 = n2; p.symmetrise = symmetrise; p.out = out;
+        const int bt = block_threads();
+        long blocks = (m * m + bt - 1) / bt;
+        const long cap = (long)dev_info().sms * 8;
+        if (blocks > cap) blocks = cap;
+        rc = launch_kernel("k_eig_assemble", k_eig_assemble, dim3((unsigned)blocks), dim3(bt), 0, st, false, p);
+    }
+#ifdef TTIPM_EMU
+    free(scratch);
+#else
+    cudaFreeAsync(scratch, st);
+#endif
+    return rc;
 }
 
 extern "C" int64_t ttipm_eig_workspace(int m, int K) {

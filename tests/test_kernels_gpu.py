@@ -138,6 +138,18 @@ def test_qr_svd_cooperative(rt):
     KC.assert_small(KC.case_qr_svd(rt, shapes=((440, 330), (165, 220), (600, 200)), graded=True), tol=1e-11)
 
 
+def test_qr_svd_beyond_one_cluster(rt):
+    """unfoldings with >= 32 block pairs per Jacobi round (the rank-exploded intermediates of the zip-up products at
+    maxcut_13) leave the 16-CTA cluster for a cooperative grid of up to 64 CTAs; both forms on the same matrix"""
+    shapes = ((700, 640), (1200, 560))
+    KC.assert_small(KC.case_qr_svd(rt, shapes=shapes), tol=1e-10)
+    old = rt.lib.ttipm_linalg_use_cluster(0)
+    try:
+        KC.assert_small(KC.case_qr_svd(rt, shapes=((220, 165), (440, 330))), tol=1e-11)      # cooperative grid below 16 CTAs too
+    finally:
+        rt.lib.ttipm_linalg_use_cluster(old)
+
+
 def test_elementwise(rt):
     KC.assert_small(KC.case_elementwise(rt), tol=1e-13)
 
