@@ -484,16 +484,22 @@ def main():
                              "bound": "hbm" if hbm_bound else "tensor", "achieved": rate,
                              "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": rate / (hbm if hbm_bound else peak)}
         dom = max(kernels, key=lambda k: kernels[k]["seconds"]) if kernels else None
-        traffic = None
+        # DRAM traffic per launch of the dominant kernel comes from an ncu capture of this same command (ncu cannot run
+        # inside the timed process): profiles/ncu_traffic.json holds the per-launch average and names the capture
+        traffic, traffic_source = None, None
         tfile = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if dom and os.path.exists(tfile):
-            traffic = json.load(open(tfile)).get(args.workload, {}).get(dom)
+            rec = json.load(open(tfile)).get(args.workload, {}).get(dom)
+            if isinstance(rec, dict):
+                traffic, traffic_source = rec.get("bytes_per_launch"), rec.get("source")
+            else:
+                traffic = rec
         roof = None
         if dom:
             kd = kernels[dom]
             roof = {"bound": kd["bound"], "kernel": KERNEL_NAMES.get(dom, dom), "achieved": kd["achieved"],
                     "peak": hbm if kd["bound"] == "hbm" else peak, "unit": kd["unit"], "frac": kd["frac"],
-                    "traffic": traffic,
+                    "traffic": traffic, "traffic_source": traffic_source,
                     "peak_source": hbm_src if kd["bound"] == "hbm" else
                     "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no fp64 figure)",
                     "launches": kd["launches"], "kernel_share_of_step": kd["share_of_step"],

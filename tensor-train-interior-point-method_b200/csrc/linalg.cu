@@ -944,11 +944,11 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
         if (mode == 0) G = npairs;                      // Jacobi keeps npairs CTAs busy
         else G = (int)((K + 7) / 8);                    // the QR phases: one warp per trailing column
         // one thread-block cluster (hardware barrier) up to 16 CTAs; unfoldings with >= 32 block pairs per round (K >= ~500:
-        // the rank-exploded intermediates of the zip-up products, src/tt_ipm.py:1074 at maxcut_13) spread over up to 64 CTAs
+        // the rank-exploded intermediates of the zip-up products, src/tt_ipm.py:1074 at maxcut_13) spread over up to 128 CTAs
         // of a cooperative grid instead
-        G = G >= 32 ? imin(G, 64) : imin(G, 16);
+        G = G >= 32 ? imin(G, 128) : imin(G, 16);
         if (g_coop_min_dim <= 1) G = imax(G, 2);        // forced (tests): always exercise the multi-CTA path
-        G = imax(1, imin(G, imin(64, di.sms)));
+        G = imax(1, imin(G, imin(128, di.sms)));
     }
     pl.grid = G;
 #ifdef TTIPM_EMU
