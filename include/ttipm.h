@@ -24,6 +24,10 @@ int ttipm_abi_version(void);
 const char* ttipm_last_error(void);
 /* number of SMs / max opt-in shared memory per block of the current device (0 on failure) */
 int ttipm_device_info(int* sm_count, int* smem_optin_bytes);
+/* Programmatic dependent launch of the library's kernels (each kernel may be scheduled while its predecessor in the
+ * stream still runs and waits in `griddepcontrol.wait`): 1 (default; TTIPM_PDL=0 in the environment disables) / 0.
+ * Returns the previous setting; a negative argument only queries. */
+int ttipm_use_pdl(int on);
 
 /* One projected operator block  P1[l,s,r] * A[s,m,n,S] * P2[L,S,R]  of the local KKT system.
  * The strides address the LOGICAL axes, so transposed / permuted operands

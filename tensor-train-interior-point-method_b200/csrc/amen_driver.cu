@@ -585,7 +585,20 @@ struct Amen {
                 Tensor dst = prev_red.select(0, q);
                 ewise(c, prev.select(1, src[q]), 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, &dst, nullptr);
             }
-            Tensor lvec = lg(prev_red, true, nullptr);
+            Tensor lvec;
+            try {
+                lvec = lg(prev_red, true, nullptr);
+            } catch (const DriverError& e) {
+                // a local block the Krylov kernel cannot take (e.g. shared-memory plan): like any exception inside the
+                // reference's local solver -- keep previous_solution, flag direct_solve_failure, let the sweep go on
+                krylov_failures++;
+                last_krylov_error = e.what();
+                o.sol = prev;
+                o.res_new = o.res_old;
+                direct_solve_failure = true;
+                local_solves++;
+                return o;
+            }
             Tensor n0, n1, diff = Tensor::empty(c, {(long)nred, r, n, R});
             ewise(c, lrhs, 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, nullptr, &n0);
             ewise(c, lrhs, 1.0, &lvec, -1.0, nullptr, 0.0, nullptr, &diff, &n1);

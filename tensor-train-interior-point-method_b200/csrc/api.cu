@@ -105,6 +105,15 @@ void* blas_handle(tt_stream_t) { return nullptr; }
 void* solver_handle(tt_stream_t) { return nullptr; }
 #endif
 
+static int g_use_pdl = -1;
+int pdl_enabled() {
+    if (g_use_pdl < 0) {
+        const char* e = getenv("TTIPM_PDL");
+        g_use_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_use_pdl;
+}
+
 int check_bound_device() {
 #ifndef TTIPM_EMU
     const DevInfo di = dev_info();
@@ -152,6 +161,11 @@ int dev_copy(void* dst, const void* src, size_t bytes, tt_stream_t st) {
 
 }  // namespace ttipm
 
+extern "C" int ttipm_use_pdl(int on) {
+    const int old = ttipm::pdl_enabled();
+    if (on >= 0) ttipm::g_use_pdl = on ? 1 : 0;
+    return old;
+}
 extern "C" int ttipm_abi_version(void) { return TTIPM_ABI_VERSION; }
 extern "C" const char* ttipm_last_error(void) { return ttipm::g_err; }
 extern "C" int ttipm_device_info(int* sm_count, int* smem_optin_bytes) {

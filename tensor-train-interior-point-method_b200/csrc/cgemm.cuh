@@ -368,6 +368,7 @@ TT_DEV void cg_tile(const CgParams& p, const CgProb& pr, int batch, int m0, int 
 
 template <int BM, int BN, int WM, int WN>
 TT_GLOBAL void __launch_bounds__(WM * WN * 32) k_cgemm(const CgParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     double* smem = (double*)smem_raw;
     const int batch = blockIdx.x / p.jobs_per_batch, job = blockIdx.x % p.jobs_per_batch;
@@ -387,6 +388,7 @@ struct CgReduceParams {
     CgProb prob[CG_MAX_PROBS];
 };
 TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_cg_reduce(const CgReduceParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     double* scratch = (double*)smem_raw;
     const int per_batch = p.cta0[p.nprob];

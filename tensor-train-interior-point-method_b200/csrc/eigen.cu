@@ -56,6 +56,7 @@ TT_DEV double eig_asm_entry(const EigAsmParams& p, int lam, int m1, int m2, int 
 }
 
 TT_GLOBAL void k_eig_assemble(const EigAsmParams p) {
+    pdl_entry();
     const long m = (long)p.l * p.n1 * p.n2 * p.L;
     const long total = m * m, stride = (long)gridDim.x * blockDim.x;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -317,6 +318,7 @@ TT_DEV double eig_pseudo(int e, int salt) {
 }
 
 TT_GLOBAL void __launch_bounds__(EIG_NT) k_eig_lanczos(const EigParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     double* smem = (double*)smem_raw;
     EigCtx c(p, smem);

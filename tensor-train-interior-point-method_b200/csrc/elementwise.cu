@@ -18,6 +18,7 @@ struct PermParams {
     int tw, tw_shift; // > 0: row-tiled variant (last axis in place), tw = threads along the last axis (power of two)
 };
 TT_GLOBAL void k_permute4(const PermParams p) {
+    pdl_entry();
     if (p.tw > 0) {
         // last axis contiguous on both sides (every permutation of the sweep): tw threads run along it, the
         // remaining threads of the CTA take further rows; one index decode per row, independent loads in flight
@@ -67,6 +68,7 @@ struct NormParams {
 };
 // one CTA per block j: out[j] = max(sqrt(sum_{rho, i} x[rho, j, i]^2), floor)
 TT_GLOBAL void k_block_norms(const NormParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     double* scr = (double*)smem_raw;
     const int j = blockIdx.x;
@@ -100,6 +102,7 @@ TT_DEV double ew_value(const EwParams& p, long ia, long ib, long ic, long iw) {
     return v;
 }
 TT_GLOBAL void k_ewise(const EwParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     double* scr = (double*)smem_raw;
     double ss = 0.0;
@@ -162,6 +165,7 @@ struct TruncParams {
 // running residual res_j = base - sum_{i >= j} Y_i, j = q-1 .. 0 ; out[j][cta] = partial ||res_j||^2
 // (reference src/tt_als.py:338-345 / :466-471 evaluated for every candidate rank at once)
 TT_GLOBAL void k_trunc_resnorms(const TruncParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     double* acc = (double*)smem_raw;   // q x nwarps
     const int nw = blockDim.x >> 5, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

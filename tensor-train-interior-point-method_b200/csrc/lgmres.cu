@@ -249,6 +249,7 @@ TT_DEV int lg_converged(const LgParams& p, int it, double rn, double& ttol, doub
 }
 
 TT_GLOBAL void __launch_bounds__(512) k_lgmres(const LgParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     double* smem = (double*)smem_raw;
     LgCtx c(p, smem);
@@ -663,6 +664,7 @@ struct LgInfoParams {
     int grid;
 };
 TT_GLOBAL void k_lg_info(const LgInfoParams p) {
+    pdl_entry();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         for (int i = 0; i < 4; ++i) p.out[i] = (double)p.ci[4 + i];
         p.out[4] = p.cd[2];

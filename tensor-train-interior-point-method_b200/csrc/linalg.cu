@@ -698,6 +698,7 @@ TT_DEV int lin_jacobi_resident(LinCtx& c, double* GJ, int K, int Mj) {
 // grid = (CTAs per matrix, batch)
 template <int NT>
 TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     double* smem = (double*)smem_raw;
     const int batch = blockIdx.y;

@@ -20,6 +20,7 @@ struct MvParams {
 
 // grid.x = nb_out * ntiles, grid.y = batch
 TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_block_matvec(const MvParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     double* smem = (double*)smem_raw;
     const MvGeom& g = p.g;
@@ -60,6 +61,7 @@ struct DiagParams {
     double* out;
 };
 TT_GLOBAL void k_local_diag(const DiagParams p) {
+    pdl_entry();
     const int total = p.l * p.nm * p.L;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int lam = i / (p.nm * p.L), mu = (i / p.L) % p.nm, Lam = i % p.L;
@@ -85,6 +87,7 @@ struct DenseParams {
     double* out;
 };
 TT_GLOBAL void k_local_dense(const DenseParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     double* W = (double*)smem_raw;   // nm*nm*S
     const int lam = blockIdx.x / p.r, rho = blockIdx.x % p.r;

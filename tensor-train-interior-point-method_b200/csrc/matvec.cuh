@@ -27,6 +27,7 @@ struct MvGeom {
     int smax, Smax;
     int ld1, ld2, ldA, ldY; // leading dimensions of T1, T2, As, Ys
     int oT1, oT2, oAs, oYs, oOffs;   // offsets in doubles from the shared base (oOffs too)
+    int stageA;             // operator core staged in shared memory (As); 0: stage 2 reads it through its strides (L2)
     int smem_bytes;
 };
 
@@ -44,6 +45,13 @@ static inline int mv_plan(MvGeom& g, int l, int L, int r, int R, int nm, int sma
     int Lt = (L * nb_out + target_ctas - 1) / target_ctas;
     if (Lt < 1) Lt = 1;
     if (Lt > L) Lt = L;
+    // The staged operator core As is (nm Smax) x (smax nm) doubles: at operator ranks of ~36 (graphm_3, late IPM
+    // iterations) it alone exceeds the shared memory of an SM.  Above a quarter of the limit stage 2 reads the core
+    // through its strides instead (a few 100 KB, L2 resident).
+    {
+        const int ldA0 = mv_pad(smax * nm, 0, 2) + ((smax * nm) % 16 == 0 ? 8 : 0);
+        g.stageA = (long)nm * Smax * ldA0 * 8 <= smem_limit / 4 ? 1 : 0;
+    }
     for (;;) {
         g.Lt = Lt;
         g.ntiles = (L + Lt - 1) / Lt;
@@ -51,7 +59,7 @@ static inline int mv_plan(MvGeom& g, int l, int L, int r, int R, int nm, int sma
         g.ld2 = mv_pad(nm * Lt, 0, 2) + ((nm * Lt) % 16 == 0 ? 8 : 0);
         g.ldA = mv_pad(smax * nm, 0, 2) + ((smax * nm) % 16 == 0 ? 8 : 0);
         g.ldY = nm * Lt;
-        int nT1 = r * Lt * g.ld1, nT2 = smax * r * g.ld2, nAs = nm * Smax * g.ldA, nYs = l * g.ldY;
+        int nT1 = r * Lt * g.ld1, nT2 = smax * r * g.ld2, nAs = g.stageA ? nm * Smax * g.ldA : 0, nYs = l * g.ldY;
         int m1 = r * nm, m2 = r * Lt, m3 = l;
         int k1 = R, k2 = nm * Smax, k3 = smax * r;
         int n1 = Lt * Smax, n2 = smax * nm, n3 = nm * Lt;
@@ -141,10 +149,12 @@ TT_DEV void mv_accumulate_term(const MvTerm& t, const double* __restrict__ x_blk
     }
 
     // operator core -> As[(nu, sig'), (sig, mu)]
-    for (int i = threadIdx.x; i < nm * S * s * nm; i += blockDim.x) {
-        const int col = i % (s * nm), row = i / (s * nm);
-        const int sg = col / nm, mu = col % nm, nu = row / S, sp = row % S;
-        As[row * ldA + col] = t.A[sg * t.as_[0] + mu * t.as_[1] + nu * t.as_[2] + sp * t.as_[3]];
+    if (g.stageA) {
+        for (int i = threadIdx.x; i < nm * S * s * nm; i += blockDim.x) {
+            const int col = i % (s * nm), row = i / (s * nm);
+            const int sg = col / nm, mu = col % nm, nu = row / S, sp = row % S;
+            As[row * ldA + col] = t.A[sg * t.as_[0] + mu * t.as_[1] + nu * t.as_[2] + sp * t.as_[3]];
+        }
     }
     // stage 1: T1[(rho, Lt), (nu, sig')] = sum_Rho x[(rho, nu), Rho] * P2[(L0 + Lt, sig'), Rho]
     tgemm(r * nm, Ltc * S, R, x_blk, ax2(nm, x_rs, x_ns), ax1(1),
@@ -155,12 +165,15 @@ TT_DEV void mv_accumulate_term(const MvTerm& t, const double* __restrict__ x_blk
           },
           offs);
     // stage 2: T2[(sig, rho), (mu, Lt)] = sum_(nu, sig') T1[(rho, Lt), (nu, sig')] * As[(nu, sig'), (sig, mu)]
-    tgemm(r * Ltc, s * nm, nm * S, T1, ax1(ld1), ax1(1), As, ax1(ldA), ax1(1),
-          [&](int m, int n, double v) {
-              const int rho = m / Ltc, lt = m % Ltc, sg = n / nm, mu = n % nm;
-              T2[(sg * r + rho) * ld2 + mu * Ltc + lt] = v;
-          },
-          offs);
+    auto store2 = [&](int m, int n, double v) {
+        const int rho = m / Ltc, lt = m % Ltc, sg = n / nm, mu = n % nm;
+        T2[(sg * r + rho) * ld2 + mu * Ltc + lt] = v;
+    };
+    if (g.stageA)
+        tgemm(r * Ltc, s * nm, nm * S, T1, ax1(ld1), ax1(1), As, ax1(ldA), ax1(1), store2, offs);
+    else        // B[(nu, sig'), (sig, mu)] = A[sig, mu, nu, sig'] straight from the core (composite strides)
+        tgemm(r * Ltc, s * nm, nm * S, T1, ax1(ld1), ax1(1), t.A, ax2(S, t.as_[2], t.as_[3]), ax2(nm, t.as_[0], t.as_[1]),
+              store2, offs);
     // stage 3: Ys[lam, (mu, Lt)] += alpha * sum_(sig, rho) P1[lam, sig, rho] * T2[(sig, rho), (mu, Lt)]
     const double alpha = t.alpha;
     tgemm(l, nm * Ltc, s * r, t.P1, ax1(t.p1s[0]), ax2(r, t.p1s[1], t.p1s[2]), T2, ax1(ld2), ax1(1),

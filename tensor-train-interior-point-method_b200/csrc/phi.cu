@@ -26,6 +26,7 @@ struct PhiParams {
 // forward : out[L',S,R'] = sum Phi[l,s,r] U[l,M,L'] A[s,M,N,S] V[r,N,R']   tile over R'
 // backward: out[l,s,r]   = sum Phi[L,S,R] U[l,M,L]  A[s,M,N,S] V[r,N,R]    tile over r
 TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_phi_update(const PhiParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     double* smem = (double*)smem_raw;
     double* T1 = smem + p.oT1;
@@ -118,6 +119,7 @@ struct RhsParams {
 };
 
 TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_rhs_contract(const RhsParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     double* smem = (double*)smem_raw;
     double* T = smem + p.oT;
@@ -172,6 +174,7 @@ struct GemmParams {
 };
 
 TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_gemm(const GemmParams p) {
+    pdl_entry();
     TT_SMEM_DECL(smem_raw);
     int* offs = (int*)smem_raw;
     const int tiles_n = (p.N + p.tn - 1) / p.tn;

@@ -14,6 +14,7 @@ struct BdParams {
 };
 // reference cy_src/tt_ops_cy.pyx:229-258
 TT_GLOBAL void k_block_diag(const BdParams p) {
+    pdl_entry();
     // rows = (i, q) of the output core, tw threads along the rank axis j; one decode per row, coalesced segments
     const int Ro = p.mode == 2 ? p.Ra : p.Ra + p.Rb;
     const int ro = p.mode == 0 ? p.ra : p.ra + p.rb;
@@ -52,6 +53,7 @@ struct EmbedParams {
 };
 // reference src/tt_ops.py:360-375, :312-316
 TT_GLOBAL void k_embed(const EmbedParams p) {
+    pdl_entry();
     const int Q = p.mode == 2 ? p.q : 4;
     const int tx = threadIdx.x & (p.tw - 1), ty = threadIdx.x >> p.tw_shift, rows_per = blockDim.x >> p.tw_shift;
     const long rows = (long)p.r * Q * Q;
@@ -81,6 +83,7 @@ struct Scale2Params {
     int rows, cols, axis, divide;   // axis 0: by row index, 1: by column index
 };
 TT_GLOBAL void k_scale2d(const Scale2Params p) {
+    pdl_entry();
     const long total = (long)p.rows * p.cols, stride = (long)gridDim.x * blockDim.x;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
         const int i = (int)(e / p.cols), j = (int)(e % p.cols);

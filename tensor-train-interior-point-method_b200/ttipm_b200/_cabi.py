@@ -34,6 +34,7 @@ class EigOp(C.Structure):
 SIGNATURES = {
     "ttipm_abi_version": (C.c_int, []),
     "ttipm_last_error": (C.c_char_p, []),
+    "ttipm_use_pdl": (C.c_int, [C.c_int]),
     "ttipm_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ttipm_block_matvec": (C.c_int, [C.POINTER(Term), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, i64, i64, i64, i64, C.c_void_p, i64, i64, i64, i64, C.c_double,

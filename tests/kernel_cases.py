@@ -437,3 +437,36 @@ def case_als_products(rt, names=ALS_CASES):
         errs[name + "_sweeps"] = 0.0 if [(t[0], t[1], t[3]) for t in tr_dev] == [(t[0], t[1], t[3]) for t in tr_orc] else 1.0
         errs[name] = rel(_dense_tt(mine), _dense_tt(ref))
     return errs
+
+
+def case_large_operator_rank(rt, r=3, R=2, s=36, ineq=True, seed=5):
+    """Operator ranks of ~36 (graphm_3 rank 2 reaches (0,1): 36 in late IPM iterations): the staged operator core no
+    longer fits shared memory, so stage 2 of the fused K1 / Krylov matvec reads the core through its strides.  Checks the
+    fused local matvec and the Schur-reduced operator (the persistent Krylov kernel's matvec) against the oracle."""
+    rng = np.random.default_rng(seed)
+    nb = 4 if ineq else 3
+    ranks = {(0, 0): (s, s - 1), (0, 1): (s, s), (1, 2): (1, 1), (2, 1): (2, 3), (2, 2): (s - 2, s)}
+    if ineq:
+        ranks.update({(3, 1): (1, 1), (3, 3): (2, 2)})
+    A = {k: rng.standard_normal((a, 4, 4, b)) for k, (a, b) in ranks.items()}
+    P1 = {k: rng.standard_normal((r, a, r)) for k, (a, b) in ranks.items()}
+    P2 = {k: rng.standard_normal((R, b, R)) for k, (a, b) in ranks.items()}
+    x = rng.standard_normal((r, nb, 4, R))
+    aliases = {(1, 2): (1, 3)} if ineq else {}
+    bm = O.BlockMatrix({k: [v] for k, v in A.items()}, aliases=aliases, transposes={(0, 1): (1, 0)})
+    errs = {}
+    old = rt.lib.ttipm_matvec_big_min_flops(1e30)            # keep the fused kernel (the grouped path has no such limit)
+    try:
+        c = dict(A=A, transposes={(0, 1): (1, 0)}, aliases=aliases)
+        y = K.block_matvec(full_terms(rt, c, P1, P2, False, False), rt.to_device(x), nb, (r, R), rt=rt)
+        errs["fused_matvec"] = rel(rt.to_host(y), O.block_local_product(bm, 0, P1, P2, x))
+    finally:
+        rt.lib.ttipm_matvec_big_min_flops(old)
+    inv_I = 1.0 / (1.0 + rng.random((r, 4, R)))
+    red = K.ReducedOperator(_dev(rt, P1), _dev(rt, A), _dev(rt, P2), rt.to_device(inv_I), ineq, rt=rt)
+    v = rng.standard_normal((3 if ineq else 2) * r * 4 * R)
+    want = (O.ReducedOperatorIneq if ineq else O.ReducedOperatorEq)(P1, A, P2, inv_I).matvec(v)
+    for grid in (1, 3):
+        got = rt.to_host(red.matvec(rt.to_device(v), grid_hint=grid)).reshape(-1)
+        errs[f"reduced_matvec_grid{grid}"] = rel(got, want)
+    return errs

@@ -184,3 +184,8 @@ def test_truncated_svd_and_kick_rank(rt):
     assert np.linalg.norm(q @ q.T - qo @ qo.T) <= 1e-12
     assert list(tt_ops.symmetric_powers_of_two(5)) == list(O.symmetric_powers_of_two(5)) == [2, 4, 8, 4, 2]
     assert list(tt_ops.symmetric_powers_of_two(4)) == [2, 4, 4, 2]
+
+
+def test_large_operator_rank(rt):
+    KC.assert_small(KC.case_large_operator_rank(rt, r=3, R=2, s=36, ineq=True))
+    KC.assert_small(KC.case_large_operator_rank(rt, r=2, R=3, s=40, ineq=False))

@@ -150,6 +150,12 @@ def test_qr_svd_beyond_one_cluster(rt):
         rt.lib.ttipm_linalg_use_cluster(old)
 
 
+@pytest.mark.parametrize("r,R,s,ineq", [(3, 2, 36, True), (42, 21, 36, True), (16, 16, 48, False)])
+def test_large_operator_rank(rt, r, R, s, ineq):
+    """graphm_3 rank 2 reaches operator ranks of 36 at (r, R) = (42, 21): stage 2 without the staged operator core"""
+    KC.assert_small(KC.case_large_operator_rank(rt, r=r, R=R, s=s, ineq=ineq))
+
+
 def test_elementwise(rt):
     KC.assert_small(KC.case_elementwise(rt), tol=1e-13)
 
