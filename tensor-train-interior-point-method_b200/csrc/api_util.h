@@ -46,7 +46,7 @@ static inline int convert_term(const ttipm_term& in, MvTerm& out) {
 }
 
 // large-rank path of K1 (cgemm.cu)
-bool mv_big_possible(int nterms, int l, int L, int nm, int nb_out);
+bool mv_big_possible(int nterms, int l, int L, int nm, int nb_out, bool want_sumsq);
 bool mv_big_wanted(const MvTerm* t, int nterms, int l, int L, int r, int R, int nm, int nb_out, int nbatch);
 int mv_big(const MvTerm* t, int nterms, int l, int L, int r, int R, int nm, int nb_out, const double* x, long x_bs,
            long x_rs, long x_ns, long x_batch, double* y, long y_bs, long y_rs, long y_ns, long y_batch, double y_scale,

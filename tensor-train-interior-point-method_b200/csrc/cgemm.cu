@@ -144,8 +144,9 @@ static int cg_run(CgParams& p, int sms, tt_stream_t st) {
     return rc;
 }
 
-bool mv_big_possible(int nterms, int l, int L, int nm, int nb_out) {
+bool mv_big_possible(int nterms, int l, int L, int nm, int nb_out, bool want_sumsq) {
     if (nterms < 1 || nterms > CG_MAX_PROBS || nb_out > CG_MAX_PROBS) return false;
+    if (!want_sumsq) return true;        // the tile-count limit below only concerns the sum-of-squares slots of the epilogue
 #ifdef TTIPM_EMU
     const int mt = 16;
 #else

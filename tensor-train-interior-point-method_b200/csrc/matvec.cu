@@ -113,6 +113,35 @@ TT_GLOBAL void k_local_dense(const DenseParams p) {
     }
 }
 
+// sum of squares of a stored y (l, nb, nm, L through strides) into slot 0 of the batch entry's partial sums: the
+// fallback of the grouped path when an output block has more tiles than sum-of-squares slots (a large left rank next to
+// a right rank of 1 or 2 at the ends of the train)
+struct SumsqParams {
+    const double* y;
+    long y_bs, y_rs, y_ns, y_batch;
+    int l, L, nm, nb;
+    double* sumsq;
+    long sumsq_batch;
+};
+TT_GLOBAL void k_sumsq_strided(const SumsqParams p) {
+    pdl_entry();
+    TT_SMEM_DECL(smem_raw);
+    double* scr = (double*)smem_raw;
+    const double* y = p.y + (long)blockIdx.x * p.y_batch;
+    const long total = (long)p.l * p.nb * p.nm * p.L;
+    double acc = 0.0;
+    for (long e = threadIdx.x; e < total; e += blockDim.x) {
+        long t = e;
+        const int Lam = (int)(t % p.L); t /= p.L;
+        const int mu = (int)(t % p.nm); t /= p.nm;
+        const int i = (int)(t % p.nb); const int lam = (int)(t / p.nb);
+        const double v = y[i * p.y_bs + lam * p.y_rs + mu * p.y_ns + Lam];
+        acc += v * v;
+    }
+    acc = block_sum(acc, scr);
+    if (threadIdx.x == 0) p.sumsq[(long)blockIdx.x * p.sumsq_batch] = acc;
+}
+
 }  // namespace ttipm
 
 using namespace ttipm;
@@ -147,10 +176,21 @@ extern "C" int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, in
     DevInfo di = dev_info();
     if (mv_plan(p.g, l, L, r, R, nmode, smax, Smax, nb_out, (di.sms * 2 + nbatch - 1) / nbatch, di.smem_optin)) {
         // the fused kernel's intermediates do not fit shared memory: the grouped-GEMM path has no such limit
-        if (mv_big_possible(nterms, l, L, nmode, nb_out))
+        if (mv_big_possible(nterms, l, L, nmode, nb_out, sumsq != nullptr))
             return mv_big(p.t, nterms, l, L, r, R, nmode, nb_out, x, x_block_stride, x_row_stride, x_mode_stride,
                           x_batch_stride, y, y_block_stride, y_row_stride, y_mode_stride, y_batch_stride, y_scale, sub,
                           sub_scale, sumsq, nbatch, (tt_stream_t)stream);
+        if (mv_big_possible(nterms, l, L, nmode, nb_out, false)) {
+            // more output tiles than sum-of-squares slots: product without the fused norm, then one pass over y
+            int rc = mv_big(p.t, nterms, l, L, r, R, nmode, nb_out, x, x_block_stride, x_row_stride, x_mode_stride,
+                            x_batch_stride, y, y_block_stride, y_row_stride, y_mode_stride, y_batch_stride, y_scale, sub,
+                            sub_scale, nullptr, nbatch, (tt_stream_t)stream);
+            if (rc) return rc;
+            SumsqParams sp{y, (long)y_block_stride, (long)y_row_stride, (long)y_mode_stride, (long)y_batch_stride, l, L, nmode,
+                           nb_out, sumsq, (long)nb_out * L};
+            return launch_kernel("k_sumsq_strided", k_sumsq_strided, dim3(nbatch), dim3(block_threads()), 40 * 8,
+                                 (tt_stream_t)stream, false, sp);
+        }
         return fail(4, "block_matvec: shape l=%d L=%d r=%d R=%d s=%d S=%d needs %d B shared memory (> %d)", l, L, r,
                     R, smax, Smax, p.g.smem_bytes, di.smem_optin);
     }

@@ -28,6 +28,7 @@ struct MvGeom {
     int ld1, ld2, ldA, ldY; // leading dimensions of T1, T2, As, Ys
     int oT1, oT2, oAs, oYs, oOffs;   // offsets in doubles from the shared base (oOffs too)
     int stageA;             // operator core staged in shared memory (As); 0: stage 2 reads it through its strides (L2)
+    int sc;                 // operator-rank chunk of stages 2 / 3: T2 holds sc of the s slices at a time (sc = smax: all)
     int smem_bytes;
 };
 
@@ -52,14 +53,16 @@ static inline int mv_plan(MvGeom& g, int l, int L, int r, int R, int nm, int sma
         const int ldA0 = mv_pad(smax * nm, 0, 2) + ((smax * nm) % 16 == 0 ? 8 : 0);
         g.stageA = (long)nm * Smax * ldA0 * 8 <= smem_limit / 4 ? 1 : 0;
     }
+    int sc = smax;
     for (;;) {
         g.Lt = Lt;
+        g.sc = sc;
         g.ntiles = (L + Lt - 1) / Lt;
         g.ld1 = mv_pad(nm * Smax, 4, 8);
         g.ld2 = mv_pad(nm * Lt, 0, 2) + ((nm * Lt) % 16 == 0 ? 8 : 0);
         g.ldA = mv_pad(smax * nm, 0, 2) + ((smax * nm) % 16 == 0 ? 8 : 0);
         g.ldY = nm * Lt;
-        int nT1 = r * Lt * g.ld1, nT2 = smax * r * g.ld2, nAs = g.stageA ? nm * Smax * g.ldA : 0, nYs = l * g.ldY;
+        int nT1 = r * Lt * g.ld1, nT2 = sc * r * g.ld2, nAs = g.stageA ? nm * Smax * g.ldA : 0, nYs = l * g.ldY;
         int m1 = r * nm, m2 = r * Lt, m3 = l;
         int k1 = R, k2 = nm * Smax, k3 = smax * r;
         int n1 = Lt * Smax, n2 = smax * nm, n3 = nm * Lt;
@@ -74,8 +77,14 @@ static inline int mv_plan(MvGeom& g, int l, int L, int r, int R, int nm, int sma
         g.oOffs = g.oYs + nYs;
         g.smem_bytes = (g.oOffs + nOffs + 40) * 8;
         if (g.smem_bytes <= smem_limit) return 0;
-        if (Lt == 1) return 1;
-        Lt = Lt / 2;
+        if (Lt > 1) {
+            Lt = Lt / 2;
+            continue;
+        }
+        // one output column per tile and still too large (left ranks of ~130 with operator ranks of ~25 at graphm_3):
+        // stages 2 and 3 run over chunks of the operator rank, T2 holds one chunk
+        if (sc == 1) return 1;
+        sc = (sc + 1) / 2;
     }
 }
 
@@ -88,7 +97,7 @@ static inline int mv_plan(MvGeom& g, int l, int L, int r, int R, int nm, int sma
 TT_DEV bool mv_term_is_small(const MvTerm& t, const MvGeom& g, int Ltc) {
     const int n1 = g.r * Ltc * g.nm * t.S, n2 = t.s * g.r * g.nm * Ltc, n3 = g.l * g.nm * Ltc;
     const int lim = 4 * (int)blockDim.x;
-    return n1 <= lim && n2 <= lim && n3 <= lim && g.R <= 32 && g.nm * t.S <= 64 && t.s * g.r <= 64;
+    return n1 <= lim && n2 <= lim && n3 <= lim && g.R <= 32 && g.nm * t.S <= 64 && t.s * g.r <= 64 && g.sc >= t.s;
 }
 TT_DEV void mv_accumulate_term_small(const MvTerm& t, const double* __restrict__ x_blk, int x_rs, int x_ns, const MvGeom& g,
                                      int L0, int Ltc, double* smem) {
@@ -164,20 +173,25 @@ TT_DEV void mv_accumulate_term(const MvTerm& t, const double* __restrict__ x_blk
               T1[(rho * Ltc + lt) * ld1 + nu * S + sp] = v;
           },
           offs);
-    // stage 2: T2[(sig, rho), (mu, Lt)] = sum_(nu, sig') T1[(rho, Lt), (nu, sig')] * As[(nu, sig'), (sig, mu)]
-    auto store2 = [&](int m, int n, double v) {
-        const int rho = m / Ltc, lt = m % Ltc, sg = n / nm, mu = n % nm;
-        T2[(sg * r + rho) * ld2 + mu * Ltc + lt] = v;
-    };
-    if (g.stageA)
-        tgemm(r * Ltc, s * nm, nm * S, T1, ax1(ld1), ax1(1), As, ax1(ldA), ax1(1), store2, offs);
-    else        // B[(nu, sig'), (sig, mu)] = A[sig, mu, nu, sig'] straight from the core (composite strides)
-        tgemm(r * Ltc, s * nm, nm * S, T1, ax1(ld1), ax1(1), t.A, ax2(S, t.as_[2], t.as_[3]), ax2(nm, t.as_[0], t.as_[1]),
-              store2, offs);
-    // stage 3: Ys[lam, (mu, Lt)] += alpha * sum_(sig, rho) P1[lam, sig, rho] * T2[(sig, rho), (mu, Lt)]
+    // stages 2 and 3 over chunks [sg0, sg0 + sn) of the operator rank (one chunk = everything unless the plan had to
+    // shrink T2):
+    //   T2[(sig, rho), (mu, Lt)] = sum_(nu, sig') T1[(rho, Lt), (nu, sig')] * A[sig, mu, nu, sig']
+    //   Ys[lam, (mu, Lt)]       += alpha * sum_(sig, rho) P1[lam, sig, rho] * T2[(sig, rho), (mu, Lt)]
     const double alpha = t.alpha;
-    tgemm(l, nm * Ltc, s * r, t.P1, ax1(t.p1s[0]), ax2(r, t.p1s[1], t.p1s[2]), T2, ax1(ld2), ax1(1),
-          [&](int m, int n, double v) { Ys[m * ldY + n] += alpha * v; }, offs);
+    for (int sg0 = 0; sg0 < s; sg0 += g.sc) {
+        const int sn = imin(g.sc, s - sg0);
+        auto store2 = [&](int m, int n, double v) {
+            const int rho = m / Ltc, lt = m % Ltc, sg = n / nm, mu = n % nm;
+            T2[(sg * r + rho) * ld2 + mu * Ltc + lt] = v;
+        };
+        if (g.stageA)
+            tgemm(r * Ltc, sn * nm, nm * S, T1, ax1(ld1), ax1(1), As + sg0 * nm, ax1(ldA), ax1(1), store2, offs);
+        else        // B[(nu, sig'), (sig, mu)] = A[sig, mu, nu, sig'] straight from the core (composite strides)
+            tgemm(r * Ltc, sn * nm, nm * S, T1, ax1(ld1), ax1(1), t.A + (long)sg0 * t.as_[0], ax2(S, t.as_[2], t.as_[3]),
+                  ax2(nm, t.as_[0], t.as_[1]), store2, offs);
+        tgemm(l, nm * Ltc, sn * r, t.P1 + (long)sg0 * t.p1s[1], ax1(t.p1s[0]), ax2(r, t.p1s[1], t.p1s[2]), T2, ax1(ld2), ax1(1),
+              [&](int m, int n, double v) { Ys[m * ldY + n] += alpha * v; }, offs);
+    }
 }
 
 TT_DEV void mv_zero_tile(const MvGeom& g, double* smem) {

@@ -470,3 +470,23 @@ def case_large_operator_rank(rt, r=3, R=2, s=36, ineq=True, seed=5):
         got = rt.to_host(red.matvec(rt.to_device(v), grid_hint=grid)).reshape(-1)
         errs[f"reduced_matvec_grid{grid}"] = rel(got, want)
     return errs
+
+
+def case_block_matvec_thin_right_rank(rt, l=70, R=2, s=25, seed=9):
+    """A large left rank next to a right rank of 1-2 with operator ranks of ~25 (the ends of the graphm_3 train in late
+    IPM iterations): the fused kernel's intermediates do not fit shared memory and an output block has more tiles than
+    sum-of-squares slots -- grouped path + a separate norm pass.  Residual form y = A x - rhs with its squared norm."""
+    rng = np.random.default_rng(seed)
+    ranks = {(0, 0): (3, 2), (0, 1): (s, s + 1), (1, 2): (1, 1), (2, 1): (s, s), (2, 2): (s - 1, s)}
+    A = {k: rng.standard_normal((a, 4, 4, b)) for k, (a, b) in ranks.items()}
+    P1 = {k: rng.standard_normal((l, a, l)) for k, (a, b) in ranks.items()}
+    P2 = {k: rng.standard_normal((R, b, R)) for k, (a, b) in ranks.items()}
+    x = rng.standard_normal((l, 3, 4, R))
+    rhs = rng.standard_normal((l, 3, 4, R))
+    bm = O.BlockMatrix({k: [v] for k, v in A.items()}, transposes={(0, 1): (1, 0)})
+    want = O.block_local_product(bm, 0, P1, P2, x) - rhs
+    c = dict(A=A, transposes={(0, 1): (1, 0)}, aliases={})
+    y, ss = K.block_matvec(full_terms(rt, c, P1, P2, False, False), rt.to_device(x), 3, (l, R), sub=rt.to_device(rhs),
+                           want_norm=True, rt=rt)
+    return {"thin_residual": rel(rt.to_host(y), want),
+            "thin_norm": abs(float(rt.to_host(ss).sum()) - float(np.sum(want ** 2))) / float(np.sum(want ** 2))}

@@ -156,6 +156,11 @@ def test_large_operator_rank(rt, r, R, s, ineq):
     KC.assert_small(KC.case_large_operator_rank(rt, r=r, R=R, s=s, ineq=ineq))
 
 
+@pytest.mark.parametrize("l,R,s", [(129, 2, 25), (129, 1, 25), (200, 2, 12)])
+def test_block_matvec_thin_right_rank(rt, l, R, s):
+    KC.assert_small(KC.case_block_matvec_thin_right_rank(rt, l=l, R=R, s=s))
+
+
 def test_elementwise(rt):
     KC.assert_small(KC.case_elementwise(rt), tol=1e-13)
 
