@@ -1,15 +1,13 @@
 """TT algebra of the IPM driver on the device.
 
 Same functions, argument meaning and mutation behaviour as the reference's cy_src/tt_ops_cy.pyx and
-the IPM-used subset of src/tt_ops.py; inputs and outputs are lists of NumPy cores (the reference's
-boundary type), the arithmetic runs in the kernels of libttipm_b200 (gemm / QR / Jacobi SVD /
-block-diagonal assembly / embeddings).  Rank decisions are taken on the host from the
-device-computed singular values with the reference's exact rule (prune_singular_vals).
-
-Functions ending in `_dev` take and return lists of device tensors, so composite operations keep
-their intermediates in HBM; the NumPy-boundary wrappers upload once and download once.
+the IPM-used subset of src/tt_ops.py.  Inputs are lists of NumPy cores (the reference's boundary
+type) or the lazy device-resident lists (`devtt.TTList`) these functions return; the arithmetic runs in
+the native TT-algebra driver of libttipm_b200 (`ttipm_tt_*`: gemm / QR / Jacobi SVD / block-diagonal
+assembly / embeddings launched back to back from C++), so a chain of TT operations keeps its
+intermediates in HBM and NumPy cores appear only when the caller looks at them.  Rank decisions use the
+reference's exact rule (prune_singular_vals) on the device-computed singular values.
 """
-import math
 from ctypes import c_double as C_double
 
 import numpy as np
@@ -116,144 +114,8 @@ def _down(tt, rt):
     return [rt.to_host(c) for c in tt]
 
 
-def tt_rl_orthogonalise_dev(tt, rt):
-    """cy_src/tt_ops_cy.pyx:132-159 on device cores (in place on the list)."""
-    d = len(tt)
-    for i in range(d - 1, 0, -1):
-        sh = tuple(tt[i].shape)
-        shm = tuple(tt[i - 1].shape)
-        Q, R = K.qr(tt[i].reshape(sh[0], -1).t(), rt=rt)            # (rest, K), (K, r)
-        nr = R.shape[0]
-        tt[i] = Q.t().contiguous().reshape(nr, *sh[1:])
-        tt[i - 1] = K.gemm(tt[i - 1].reshape(-1, sh[0]), R.t(), rt=rt).reshape(*shm[:-1], nr)
-    return tt
-
-
-def _round_sweep_dev(tt, eps, rt, collect=False):
-    """Left-to-right truncation sweep of cy_src/tt_ops_cy.pyx:197-224 / :283-318 / :349-384."""
-    d = len(tt)
-    rank = 1
-    dropped = 0.0
-    for idx in range(d - 1):
-        sh = tuple(tt[idx].shape)
-        shn = tuple(tt[idx + 1].shape)
-        U, S, W = K.svd_left(tt[idx].reshape(rank * int(np.prod(sh[1:-1])), -1), rt=rt)
-        s = rt.to_host(S)
-        if collect:
-            sc = np.cumsum(np.abs(s[::-1]) ** 2)[::-1]
-            nr = max(int(np.argmax(sc < eps ** 2)), 1)
-            if sc[-1] > eps ** 2:
-                nr = s.size
-            if nr < s.size:
-                dropped += float(sc[nr])
-        else:
-            nr = prune_singular_vals(s, eps)
-        tt[idx] = U[:, :nr].contiguous().reshape(rank, *sh[1:-1], nr)
-        tt[idx + 1] = K.gemm(W[:nr], tt[idx + 1].reshape(shn[0], -1), rt=rt).reshape(nr, *shn[1:-1], shn[-1])
-        rank = nr
-    return dropped
-
-
 def _all_rank_one(tt):
     return len(tt) == 1 or all(r == 1 for r in tt_ranks(tt))
-
-
-def tt_add_dev(a, b, rt):
-    """cy_src/tt_ops_cy.pyx:244-258 on device cores."""
-    if len(a) == 1:
-        return [K.ewise(a[0], 1.0, b=b[0], beta=1.0, rt=rt)]
-    out = []
-    last = len(a) - 1
-    for k, (x, y) in enumerate(zip(a, b)):
-        out.append(K.block_diag(x, y, "first" if k == 0 else ("last" if k == last else "mid"), rt=rt))
-    return out
-
-
-def tt_inner_prod_dev(a, b, rt):
-    """cy_src/tt_ops_cy.pyx:506-520: running (r1, r2) matrix, two GEMMs per core; returns a 1x1 device tensor."""
-    res = rt.to_device(np.ones((1, 1)))
-    for c1, c2 in zip(a, b):
-        r1, R1 = c1.shape[0], c1.shape[-1]
-        r2, R2 = c2.shape[0], c2.shape[-1]
-        nn = c1.numel() // (r1 * R1)
-        T = K.gemm(res.t(), c1.reshape(r1, nn * R1), rt=rt)                         # (r2, n R1)
-        res = K.gemm(T.reshape(r2 * nn, R1).t(), c2.reshape(r2 * nn, R2), rt=rt)    # (R1, R2)
-    return res
-
-
-def _swap_cores_dev(ca, cb, eps, rt):
-    """cy_src/tt_ops_cy.pyx:393-426."""
-    if ca.dim() == 3:
-        a0, a1, a2 = ca.shape
-        b0, b1, b2 = cb.shape
-        t = K.gemm(ca.reshape(a0 * a1, a2), cb.reshape(b0, b1 * b2), rt=rt).reshape(a0, a1, b1, b2)
-        t = K.permute4(t, (0, 2, 1, 3), rt=rt)                                      # (a0, b1, a1, b2)
-        U, S, W = K.svd_left(t.reshape(a0 * b1, a1 * b2), rt=rt)
-        rp = prune_singular_vals(rt.to_host(S), eps)
-        # reference keeps u*s on the left and v on the right; W = s*v, so rescale: left = U*s, right = W/s
-        left = K.scale_cols(U[:, :rp], S[:rp], rt=rt).reshape(a0, b1, rp)
-        right = K.scale_rows(W[:rp], S[:rp], divide=True, rt=rt).reshape(rp, a1, b2)
-        return left, right
-    a0, a1, a2, a3 = ca.shape
-    b0, b1, b2, b3 = cb.shape
-    t = K.gemm(ca.reshape(a0 * a1 * a2, a3), cb.reshape(b0, b1 * b2 * b3), rt=rt).reshape(a0, a1 * a2, b1 * b2, b3)
-    t = K.permute4(t, (0, 2, 1, 3), rt=rt)                                          # (a0, (b1 b2), (a1 a2), b3)
-    U, S, W = K.svd_left(t.reshape(a0 * b1 * b2, a1 * a2 * b3), rt=rt)
-    rp = prune_singular_vals(rt.to_host(S), eps)
-    left = K.scale_cols(U[:, :rp], S[:rp], rt=rt).reshape(a0, b1, b2, rp)
-    right = K.scale_rows(W[:rp], S[:rp], divide=True, rt=rt).reshape(rp, a1, a2, b3)
-    return left, right
-
-
-def _zipup_dev(first_fn, d, cores, eps, rt):
-    loop_eps = eps / math.sqrt(d - 1) if d > 1 else eps
-    for i in range(d):
-        cores[0] = first_fn(d - 1 - i, cores[0])
-        if i != d - 1:
-            for j in range(i, -1, -1):
-                cores[j], cores[j + 1] = _swap_cores_dev(cores[j], cores[j + 1], loop_eps, rt)
-    return cores
-
-
-def tt_fast_matrix_vec_mul_dev(M, v, eps, rt):
-    """cy_src/tt_ops_cy.pyx:430-447."""
-    cores = [c.permute(2, 1, 0).contiguous() for c in reversed(v)]
-
-    def first(p, c0):       # tensordot(M[p] (s,m,n,S), c0 (S,n,K), axes=([3,2],[0,1])) -> (s, m, K)
-        s, m, n, S = M[p].shape
-        Kk = c0.shape[2]
-        Mp = K.permute4(M[p], (0, 1, 3, 2), rt=rt).reshape(s * m, S * n)
-        return K.gemm(Mp, c0.reshape(S * n, Kk), rt=rt).reshape(s, m, Kk)
-    return _zipup_dev(first, len(M), cores, eps, rt)
-
-
-def tt_fast_mat_mat_mul_dev(A, B, eps, rt):
-    """cy_src/tt_ops_cy.pyx:451-464."""
-    cores = [c.permute(3, 1, 2, 0).contiguous() for c in reversed(B)]
-
-    def first(p, c0):       # tensordot(A[p] (s,m,n,S), c0 (S,n,j,K), axes=([3,2],[0,1])) -> (s, m, j, K)
-        s, m, n, S = A[p].shape
-        j, Kk = c0.shape[2], c0.shape[3]
-        Ap = K.permute4(A[p], (0, 1, 3, 2), rt=rt).reshape(s * m, S * n)
-        return K.gemm(Ap, c0.reshape(S * n, j * Kk), rt=rt).reshape(s, m, j, Kk)
-    return _zipup_dev(first, len(A), cores, eps, rt)
-
-
-def tt_fast_hadamard_dev(a, b, eps, rt):
-    """cy_src/tt_ops_cy.pyx:468-502: out[r, i.., K] = sum_R a[r, i.., R] c0[R, i.., K] (batched over the mode)."""
-    four = a[0].dim() == 4 and b[0].dim() == 4
-    cores = [(c.permute(3, 1, 2, 0) if four else c.permute(2, 1, 0)).contiguous() for c in reversed(b)]
-
-    def first(p, c0):
-        ap = a[p]
-        r, Rr, Kk = ap.shape[0], ap.shape[-1], c0.shape[-1]
-        nn = ap.numel() // (r * Rr)
-        A3 = ap.reshape(r, nn, Rr).permute(1, 0, 2)          # (mode, r, R) strided view
-        B3 = c0.reshape(Rr, nn, Kk).permute(1, 0, 2)         # (mode, R, K)
-        out = K.gemm(A3, B3, rt=rt)                          # (mode, r, K)
-        out = K.permute4(out.reshape(1, nn, r, Kk), (0, 2, 1, 3), rt=rt)
-        return out.reshape(r, *ap.shape[1:-1], Kk)
-    return _zipup_dev(first, len(a), cores, eps, rt)
 
 
 # ---- NumPy-boundary API (reference signatures) -----------------------------------------------------
@@ -410,15 +272,6 @@ def tt_mat_mat_mul(mat1, mat2, op_tol, eps, verbose=False):
         return out
     from .als_product import tt_approx_mat_mat_mul
     return tt_approx_mat_mat_mul(mat1, mat2, tol=op_tol, verbose=verbose)
-
-
-def _round_dev_to_host(dev, eps, rt):
-    if _all_rank_one(dev):
-        return _down(dev, rt)
-    eps = eps / np.sqrt(len(dev) - 1)
-    dev = tt_rl_orthogonalise_dev(dev, rt)
-    _round_sweep_dev(dev, eps, rt)
-    return _down(dev, rt)
 
 
 def _embed(tt, kind):
