@@ -165,6 +165,11 @@ int ttipm_linalg_block_rows(int nb);
  * which is what the rank decisions of the AMEn sweep were validated with.  Returns the previous factor; a negative
  * argument only queries. */
 double ttipm_linalg_noise_floor(double factor);
+/* The Jacobi iteration stops after a sweep whose rotations were all "small" (inner product below 1e-11 |a| |b| and sine
+ * below 1e-6): such a sweep leaves every pair orthogonal to ~1e-15, so the all-skip sweep that would only confirm
+ * convergence is not run (one sweep of ~9 on the AMEn unfoldings).  1 (default) / 0 = always run the confirming sweep.
+ * Returns the previous setting; a negative argument only queries. */
+int ttipm_linalg_early_exit(int on);
 
 /* Householder QR, A (M x N, strided) = Q (M x K) R (K x N), K = min(M, N); Q, R contiguous row-major.
  * Replaces scipy.linalg.qr(mode="economic") at reference cy_src/tt_ops_cy.pyx:147, src/tt_als.py:358, :482.

@@ -38,6 +38,7 @@
 namespace ttipm {
 
 #define TT_QR_PB 8
+#define TT_LIN_HDR 72          // doubles of per-batch flags ahead of the batch workspaces
 #define TT_LIN_REG 16          // register-resident vector length = 32 * TT_LIN_REG
 
 struct LinParams {
@@ -49,7 +50,7 @@ struct LinParams {
     double* S;
     double* Wt;
     int* info;           // 16 ints per batch entry or NULL
-    double* ws;          // [nbatch x 40 doubles: sweep flags + barrier][nbatch x ws_per]
+    double* ws;          // [nbatch x TT_LIN_HDR doubles: sweep flags (ints 0..59), barrier (64..), big-rotation flags (80..139)][nbatch x ws_per]
     long ws_per;
     long oW1, oTau1, oW2, oTau2, oG, oJt, oSv;      // offsets inside one batch workspace
     long oW3, oTau3;     // third factor of the tall SVD
@@ -67,6 +68,7 @@ struct LinParams {
     int ldk;             // leading dimension of the K x K factors W2, W3 (even)
     int ldg;             // row stride of the Jacobi rows [R (K) | accumulator (Mj) | pad], global and shared (even)
     int cluster;         // the grid is one thread-block cluster: hardware barrier between phases
+    int early_exit;      // stop after a sweep whose rotations were all small (lin_rot_level)
     int nbatch;
 };
 
@@ -387,7 +389,18 @@ TT_DEV void lin_apply_q(LinCtx& c, const double* W, const double* tau, int ld, i
 // RELATIVE accuracy cost 27-31 sweeps instead of the ~10 the significant part needs).  U stays orthonormal and
 // U * W = A holds regardless (only rotations are applied); singular values above the floor are unaffected, the ones
 // below it carry an absolute error of eps * sigma_max like LAPACK's.
-TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, double floor2, int lane) {
+// Rotation level of a pair step: 0 = none, 1 = a "small" rotation, 3 = a rotation that can still move other pairs.
+// A sweep in which every rotation was small -- inner product below 1e-11 |a| |b| AND sine below 1e-6 -- leaves every
+// pair it touched orthogonal to <= K * 1e-17 < tol (each later rotation perturbs an inner product by its sine times
+// another inner product of the same size), so the iteration stops without the extra all-skip sweep that would only
+// confirm it (one sweep of ~9 on the sweep's unfoldings).
+#define TT_JAC_SMALL_RATIO2 1e-22
+#define TT_JAC_SMALL_SIN2 1e-12
+TT_DEV int lin_rot_level(double saa, double sbb, double sab, double sn) {
+    return (sab * sab > TT_JAC_SMALL_RATIO2 * saa * sbb || sn * sn > TT_JAC_SMALL_SIN2) ? 3 : 1;
+}
+
+TT_DEV int lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, double floor2, int lane) {
     double saa = 0.0, sbb = 0.0, sab = 0.0, taa = 0.0, tbb = 0.0, tab = 0.0;
     int i0 = lane;
     for (; i0 + 32 < K; i0 += 64) {
@@ -420,7 +433,7 @@ TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, 
     sbb = warp_sum(sbb);
     sab = warp_sum(sab);
 #endif
-    if (!(sab * sab > tol2 * saa * sbb) || fmin(saa, sbb) <= floor2) return false;
+    if (!(sab * sab > tol2 * saa * sbb) || fmin(saa, sbb) <= floor2) return 0;
     // tan of the rotation angle: zeta = (sbb - saa) / (2 sab), tg = sign(zeta) / (|zeta| + sqrt(1 + zeta^2))
     double cs, sn;
     lin_rotation(saa, sbb, sab, cs, sn);
@@ -431,7 +444,7 @@ TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, 
         ra[i] = c1 * x + s1 * y;
         rb[i] = c2 * x + s2 * y;
     }
-    return true;
+    return lin_rot_level(saa, sbb, sab, sn);
 }
 
 // Cross pairs of two row blocks held in shared memory (block a: slots 0..nb-1, block b: slots nb..2nb-1).  Warp i
@@ -439,9 +452,9 @@ TT_DEV bool lin_jacobi_pair(double* ra, double* rb, int K, int Ls, double tol2, 
 // the shared-memory traffic of a step is one read and one write of the b row (the smem-only form moves 2.5x as much
 // and was bound by shared-memory bandwidth).  NQ = register chunks per row (32 * NQ >= Ls).
 template <int NQ, bool RB_REGS>
-TT_DEV bool lin_cross_pairs_reg(double* rowsS, int nb, int na, int nbb, int K, int Ls, int ldg, double tol2, double floor2,
+TT_DEV int lin_cross_pairs_reg(double* rowsS, int nb, int na, int nbb, int K, int Ls, int ldg, double tol2, double floor2,
                                 int lane, int wid, int nw) {
-    bool rot = false;
+    int rot = 0;
     for (int i0 = 0; i0 < nb; i0 += nw) {                 // one pass when the CTA has at least nb warps
         const int i = i0 + wid;
         const bool have = i < na;
@@ -502,7 +515,7 @@ TT_DEV bool lin_cross_pairs_reg(double* rowsS, int nb, int na, int nbb, int K, i
                         ra[q] = cs * x - sn * y;
                         if (e < Ls) rbp[e] = sn * x + cs * y;
                     }
-                    rot = true;
+                    rot |= lin_rot_level(saa, sbb, sab, sn);
                 }
             }
             __syncthreads();
@@ -564,7 +577,8 @@ TT_DEV int lin_jacobi(LinCtx& c, double* GJ, int K, int Mj, int* flags, long lon
                 __syncthreads();
                 // the rows of a block are contiguous: one bulk copy per block (slot q < nb -> block a, nb + q -> block b)
                 if (threadIdx.x == 0) {
-                    *rotated = 0;
+                    rotated[0] = 0;
+                    rotated[1] = 0;
                     const unsigned ba = (unsigned)(na * ldg) * 8u, bb = (unsigned)(nbb * ldg) * 8u;
                     fence_proxy_async();
                     mbar_expect_tx(c.mbar, ba + bb);
@@ -574,7 +588,7 @@ TT_DEV int lin_jacobi(LinCtx& c, double* GJ, int K, int Mj, int* flags, long lon
                 mbar_wait(c.mbar, c.mphase);
                 c.mphase ^= 1u;
                 const long long t1 = lin_now();
-                bool rot = false;
+                int rot = 0;
                 if (t == 0 && nb > 1) {
                     // intra-block pairs of both blocks: round-robin over the nb (even) slots of each block
                     const int half = nb / 2;
@@ -615,15 +629,19 @@ TT_DEV int lin_jacobi(LinCtx& c, double* GJ, int K, int Mj, int* flags, long lon
                         }
                     }
                 }
-                if (rot && lane == 0) *rotated = 1;
+                if (rot && lane == 0) rotated[0] = 1;
+                if ((rot & 2) && lane == 0) rotated[1] = 1;
                 __syncthreads();
                 const long long t2 = lin_now();
-                if (*rotated) {
+                if (rotated[0]) {
                     double* ga = GJ + (long)a * nb * ldg;
                     double* gb = GJ + (long)b * nb * ldg;
                     for (int i = threadIdx.x; i < na * ldg; i += blockDim.x) ga[i] = rowsS[i];
                     for (int i = threadIdx.x; i < nbb * ldg; i += blockDim.x) gb[i] = rowsS[(long)nb * ldg + i];
-                    if (threadIdx.x == 0) flags[sweeps] = 1;
+                    if (threadIdx.x == 0) {
+                        flags[sweeps] = 1;
+                        if (rotated[1]) flags[80 + sweeps] = 1;
+                    }
                 }
                 tm[0] += t1 - t0;
                 tm[1] += t2 - t1;
@@ -636,7 +654,8 @@ TT_DEV int lin_jacobi(LinCtx& c, double* GJ, int K, int Mj, int* flags, long lon
             tm[2] += t4 - t3;
             tm[3] += lin_now() - t4;
         }
-        if (ld_cg_i(&flags[sweeps]) == 0) {
+        // done: nothing rotated, or only small rotations (see lin_rot_level)
+        if (ld_cg_i(&flags[sweeps]) == 0 || (c.p.early_exit && ld_cg_i(&flags[80 + sweeps]) == 0)) {
             ++sweeps;
             break;
         }
@@ -666,9 +685,12 @@ TT_DEV int lin_jacobi_resident(LinCtx& c, double* GJ, int K, int Mj) {
     int sweeps = 0;
     for (; sweeps < 60;) {
         __syncthreads();
-        if (threadIdx.x == 0) *rotated = 0;
+        if (threadIdx.x == 0) {
+            rotated[0] = 0;
+            rotated[1] = 0;
+        }
         __syncthreads();
-        bool rot = false;
+        int rot = 0;
         for (int u = 0; u < Ke - 1; ++u) {
             for (int q = wid; q < half; q += nw) {
                 int x, y;
@@ -685,10 +707,11 @@ TT_DEV int lin_jacobi_resident(LinCtx& c, double* GJ, int K, int Mj) {
             }
             __syncthreads();
         }
-        if (rot && lane == 0) *rotated = 1;
+        if (rot && lane == 0) rotated[0] = 1;
+        if ((rot & 2) && lane == 0) rotated[1] = 1;
         __syncthreads();
         ++sweeps;
-        if (*rotated == 0) break;
+        if (rotated[0] == 0 || (c.p.early_exit && rotated[1] == 0)) break;
     }
     for (int i = threadIdx.x; i < K * ldg; i += blockDim.x) GJ[i] = rowsS[i];
     c.sync();
@@ -702,9 +725,9 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
     TT_SMEM_DECL(smem_raw);
     double* smem = (double*)smem_raw;
     const int batch = blockIdx.y;
-    int* flags = (int*)(p.ws + (long)batch * 40);
+    int* flags = (int*)(p.ws + (long)batch * TT_LIN_HDR);
     LinCtx c(p, smem, (unsigned*)(flags + 64));
-    double* ws = p.ws + (long)p.nbatch * 40 + (long)batch * p.ws_per;
+    double* ws = p.ws + (long)p.nbatch * TT_LIN_HDR + (long)batch * p.ws_per;
     if (p.oPg >= 0) c.panel = ws + p.oPg;
     const double* A = p.A + (long)batch * p.a_bs;
     const int M = p.M, N = p.N, K = imin(M, N), M1 = p.M1, Mj = p.Mj, ld1 = p.ld1, ldk = p.ldk, ldg = p.ldg;
@@ -859,6 +882,7 @@ static int g_coop_threads = 256;
 static int g_use_cluster = 1;
 static int g_wide_cta_min_dim = 96;
 static int g_min_block_rows = 8;
+static int g_early_exit = 1;
 
 struct LinPlan {
     LinParams p;
@@ -877,6 +901,7 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
     const bool wide = mode == 0 && M < N;
     p.M = M; p.N = N; p.mode = mode; p.nbatch = nbatch;
     p.floor_factor = g_floor_factor;
+    p.early_exit = g_early_exit;
     p.M1 = wide ? N : M;
     p.N1 = wide ? M : N;
     // three QR factorisations pay off through the sweep count of graded unfoldings; below ~16 columns the sweeps are few
@@ -920,7 +945,7 @@ static int lin_plan(LinPlan& pl, int mode, int M, int N, int nbatch) {
     p.oPg = -1;
     if (panel_global) { p.oPg = o; o += (long)TT_QR_PB * p.ldp; }
     p.ws_per = even_up(o);
-    pl.ws_total = (long)nbatch * 40 + (long)nbatch * p.ws_per;
+    pl.ws_total = (long)nbatch * TT_LIN_HDR + (long)nbatch * p.ws_per;
     const long ldg = p.ldg;
     const long qr_doubles = p.oP + (panel_global ? 0 : (long)TT_QR_PB * p.ldp);
     // Jacobi block rows: 8, raised (even) until the block pairs of a round fit one thread-block cluster of 16 CTAs,
@@ -996,7 +1021,7 @@ static int lin_launch(int mode, const double* A, long a_rs, long a_cs, long a_bs
     p.A = A; p.a_rs = a_rs; p.a_cs = a_cs; p.a_bs = a_bs;
     p.U = U; p.S = S; p.Wt = Wt; p.info = info; p.ws = ws;
     if (((uintptr_t)ws & 15) != 0) return fail(1, "linalg: workspace must be 16-byte aligned");
-    if (dev_memset(ws, 0, (size_t)nbatch * 40 * 8, st)) return fail(5, "linalg: memset failed");
+    if (dev_memset(ws, 0, (size_t)nbatch * TT_LIN_HDR * 8, st)) return fail(5, "linalg: memset failed");
     if (pl.threads == 384) return lin_launch_t<384>(pl, nbatch, st);
     return lin_launch_t<512>(pl, nbatch, st);
 }
@@ -1033,6 +1058,12 @@ extern "C" int ttipm_linalg_block_rows(int nb) {
 extern "C" int ttipm_linalg_tall_triple_qr(int on) {
     const int old = g_tall_triple_qr;
     if (on >= 0) g_tall_triple_qr = on ? 1 : 0;
+    return old;
+}
+
+extern "C" int ttipm_linalg_early_exit(int on) {
+    const int old = g_early_exit;
+    if (on >= 0) g_early_exit = on ? 1 : 0;
     return old;
 }
 

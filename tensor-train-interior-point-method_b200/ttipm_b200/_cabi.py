@@ -86,6 +86,7 @@ SIGNATURES = {
     "ttipm_cgemm_force_cfg": (C.c_int, [C.c_int]),
     "ttipm_cgemm_vector_loads": (C.c_int, [C.c_int]),
     "ttipm_linalg_noise_floor": (C.c_double, [C.c_double]),
+    "ttipm_linalg_early_exit": (C.c_int, [C.c_int]),
     "ttipm_linalg_tall_triple_qr": (C.c_int, [C.c_int]),
     "ttipm_linalg_block_rows": (C.c_int, [C.c_int]),
     "ttipm_linalg_threads": (C.c_int, [C.c_int]),

@@ -73,6 +73,8 @@ def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     if "--single-qr" in sys.argv:
         rt.lib.ttipm_linalg_tall_triple_qr(0)       # tall matrices: one QR instead of three before the Jacobi sweeps
+    if "--no-early-exit" in sys.argv:
+        rt.lib.ttipm_linalg_early_exit(0)           # always run the confirming all-skip sweep (round-2 behaviour)
     for a in sys.argv[1:]:
         if a.startswith("--nb="):
             rt.lib.ttipm_linalg_block_rows(int(a[5:]))

@@ -25,6 +25,9 @@ def main():
     g = G.load_amen(f)
     rt = get_runtime()
     for fac in [float(v) for v in sys.argv[2:]]:
+        if fac < 0:                         # negative: toggle the early exit of the Jacobi iteration off, floor 0
+            rt.lib.ttipm_linalg_early_exit(0)
+            fac = 0.0
         if fac >= 256:                      # 256 / 512: threads per CTA of the QR / SVD kernel instead of a floor factor
             rt.lib.ttipm_linalg_threads(int(fac))
             fac = 0.0
