@@ -7,7 +7,10 @@
 // (residual norms, singular values, truncation norms) through a pinned staging buffer.  The Python layer
 // (ttipm_b200.amen) only uploads the operands, makes the reference's NumPy RNG draws and fetches the result.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <algorithm>
 #include "tensor.h"
 #include "drv_ops.h"
@@ -310,6 +313,22 @@ struct Dense {
 // ---------------------------------------------------------------------------------------------------
 // the solver object
 // ---------------------------------------------------------------------------------------------------
+// TTIPM_AMEN_LOG=1: one stderr line per core step of a sweep (wall clock, shapes, residuals, which local solver ran) --
+// for runs that do not come back (e2e graphm_3), off by default and free when off
+static bool amen_log_on() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("TTIPM_AMEN_LOG");
+        on = (e && e[0] && e[0] != '0') ? 1 : 0;
+    }
+    return on == 1;
+}
+static double amen_wall_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 struct Amen {
     Ctx c;
     int d = 0, bs = 0;
@@ -528,6 +547,15 @@ struct Amen {
         return sol;
     }
 
+    void log_phase(const char* what) {             // TTIPM_AMEN_LOG: drain the stream, say which phase just finished
+        if (!amen_log_on()) return;
+        double probe = 0.0;
+        Tensor t = Tensor::empty(c, {1});
+        dev_memset(t.p, 0, sizeof(double), c.st);
+        to_host(c, t.p, 1, &probe);
+        fprintf(stderr, "[amen]   %.1f ms: %s\n", amen_wall_ms(), what);
+    }
+
     LocalOut solve_local(int k, const Tensor& prev, int size_limit, bool dense_ok, const Terms& full) {
         const long r = prev.d[0], n = prev.d[2], R = prev.d[3], m = r * n * R;
         const double rtol = 1e-5;
@@ -536,8 +564,10 @@ struct Amen {
         Tensor rhs_ss, res_ss;
         ewise(c, o.rhs, 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, nullptr, &rhs_ss);
         Tensor inv_I = local_diag_inv(c, XAX[k].at({1, 2}), A.at({1, 2})[k], XAX[k + 1].at({1, 2}));
+        log_phase("rhs block, diagonal");
         block_matvec(c, full, prev, false, bs, r, R, &o.rhs, 1.0, -1.0, &res_ss);
         std::vector<double> sums = host_sums(c, {&rhs_ss, &res_ss});
+        log_phase("residual of the previous solution");
         o.norm_rhs = std::max(sqrt(sums[0]), 1e-10);
         o.res_old = sqrt(sums[1]) / o.norm_rhs;
         const double limit = ineq ? 0.95 * size_limit : (double)size_limit;
@@ -585,9 +615,11 @@ struct Amen {
                 Tensor dst = prev_red.select(0, q);
                 ewise(c, prev.select(1, src[q]), 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, &dst, nullptr);
             }
+            log_phase("reduced right-hand side");
             Tensor lvec;
             try {
                 lvec = lg(prev_red, true, nullptr);
+                log_phase("reduced operator applied to the previous solution");
             } catch (const DriverError& e) {
                 // a local block the Krylov kernel cannot take (e.g. shared-memory plan): like any exception inside the
                 // reference's local solver -- keep previous_solution, flag direct_solve_failure, let the sweep go on
@@ -636,6 +668,7 @@ struct Amen {
 #ifndef TTIPM_EMU
             if (profile) cudaEventRecord(pr.e1, c.st);
 #endif
+            log_phase("Krylov solve");
             if (krylov_failed) {
 #ifndef TTIPM_EMU
                 if (profile) {
@@ -668,6 +701,7 @@ struct Amen {
         Tensor new_ss;
         block_matvec(c, full, o.sol, false, bs, r, R, &o.rhs, 1.0, -1.0, &new_ss);
         std::vector<double> s2 = host_sums(c, {&new_ss});
+        log_phase("residual of the new solution");
         const double res_new = sqrt(s2[0]) / o.norm_rhs;
         if (!(res_new <= o.res_old)) o.sol = prev;           // also keeps prev when res_new is not finite
         o.res_new = std::isfinite(res_new) ? std::min(o.res_old, res_new) : o.res_old;
@@ -726,10 +760,21 @@ struct Amen {
             Tensor sol, resz, rhs;
             double r_new = 0.0, norm_rhs = 1.0;
             Terms full;
+            const double t_step = amen_log_on() ? amen_wall_ms() : 0.0;
             if (solving) {
                 Tensor prev = x[k];
                 full = full_terms(k);
+                const long lg0 = lgmres_calls, dn0 = dense_solves, kf0 = krylov_failures;
                 LocalOut lo = solve_local(k, prev, 3 * d, !direct_solve_failure, full);
+                if (amen_log_on()) {
+                    std::vector<double> inf(6, 0.0);
+                    if (lgmres_calls > lg0) inf = read_vec(c, lg_infos.back());
+                    fprintf(stderr, "[amen] swp %d k %d r %ld R %ld n %ld: local solve %.1f ms (%s%s) res %.3e -> %.3e"
+                                    " krylov its %.0f matvecs %.0f reason %.0f grid %.0f\n",
+                            swp, k, r_k, R_k, n, amen_wall_ms() - t_step, dense_solves > dn0 ? "dense " : "",
+                            lgmres_calls > lg0 ? "krylov" : (krylov_failures > kf0 ? "krylov FAILED" : ""), lo.res_old,
+                            lo.res_new, inf[0], inf[1], inf[2], inf[5]);
+                }
                 sol = lo.sol; rhs = lo.rhs; r_new = lo.res_new; norm_rhs = lo.norm_rhs;
                 trace.insert(trace.end(), {(double)swp, (double)k, lo.res_old, lo.res_new, (double)(r_k * R_k)});
                 local_res = std::max(local_res, lo.res_old);
@@ -848,6 +893,12 @@ struct Amen {
                 rx[k + 1] = r;
             }
             update_interfaces(k, bck, false);
+            if (amen_log_on()) {
+                double probe = 0.0;
+                to_host(c, x[k].p, 1, &probe);             // drain the stream: the time below is the step's device time
+                fprintf(stderr, "[amen] swp %d k %d: step %.1f ms, unfolding %ld x %ld, new rank %ld\n", swp, k,
+                        amen_wall_ms() - t_step, mat.d[0], mat.d[1], r);
+            }
             if (amen && !last) {
                 const long kr = std::min<long>(kick_rank, std::min(rzm.d[0], rzm.d[1]));
                 Tensor Uz, Sz, Wz;

@@ -602,11 +602,18 @@ static int lg_setup(LgParams& p, int ineq, const ttipm_term* K00, const ttipm_te
                  2.0 * r * nmode * R * r * src[i]->s;
     int G = grid_hint > 0 ? grid_hint : (flops < 4e5 ? 1 : di.sms);
     if (G > di.sms) G = di.sms;
+    // the Hessenberg / Givens arrays sit behind the matvec's carve-up: the matvec plan must leave room for them (a plan
+    // that filled the shared memory to the last KB made the loop below alternate between G = items and 2 G forever:
+    // graphm_3, IPM iteration 4, local block r = 150, R = 16, operator ranks 30)
+    const int hess_bytes = (5 * (max_k + 2) + 4 + 2) * 8;
+    int last_G = -1;
     for (;;) {
-        if (mv_plan(p.g, r, R, r, R, nmode, smax, Smax, p.nslotA, G, di.smem_optin - 1024))
+        if (mv_plan(p.g, r, R, r, R, nmode, smax, Smax, p.nslotA, G, di.smem_optin - 1024 - hess_bytes))
             return fail(4, "lgmres: local block r=%d R=%d s=%d does not fit in shared memory", r, R, smax);
         const int items = p.nslotA * p.g.ntiles;
         if (grid_hint <= 0 && G > items) G = items;
+        if (G == last_G) return fail(4, "lgmres: no grid fits the shared memory for r=%d R=%d s=%d", r, R, smax);
+        last_G = G;
         p.ch = (p.nv + G - 1) / G;
         p.oW = 0;
         p.oH = p.ch + (p.ch & 1);

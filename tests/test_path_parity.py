@@ -228,3 +228,28 @@ def test_matvec_wrappers_reference_signature_gpu():
 
 def test_matvec_wrappers_reference_signature_emu():
     _wrappers(rt_util.emu_runtime())
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_graphm3_iteration4_predictor_system_returns():
+    """The KKT system of graphm_3 rank 2 (seed 256) at IPM iteration 4, dumped from the end-to-end run of the unmodified
+    reference driver on the B200 (oracle/ref_harness/run_dropin_ipm.py --dump-latest): solution ranks up to 129, KKT
+    operator ranks up to 36, local blocks of (r, R) = (150, 16).  There the matvec plan of the Krylov kernel filled the
+    shared memory to the last KB and lg_setup() looped forever on the host (the end-to-end run never came back from this
+    call).  No reference output exists for this system (the CPU reference needs hours to get here): the test pins that
+    the call returns, in the sweep budget, with a solution whose GLOBAL residual -- evaluated independently through the
+    containers' block_product -- is at the tolerance."""
+    from ttipm_b200 import tt_als, use_runtime
+    rt = rt_util.cuda_runtime()
+    g = G.load_amen(os.path.join(os.path.dirname(G.amen_files("amen_*")[0]), "big_graphm_3_r2_s256_it4_predictor.npz"))
+    A, b = _containers(g)
+    np.random.set_state(g["rng_state"])
+    stats = {}
+    with use_runtime(rt):
+        x, res = tt_als.tt_restarted_block_amen(A, b, g["rank_restriction"], g["op_tol"], termination_tol=g["termination_tol"],
+                                                eps=g["eps"], num_restarts=g["num_restarts"], inner_m=g["inner_m"],
+                                                x0=[c.copy() for c in g["x0"]], local_solver=_solver_stub(g["ineq"]),
+                                                _stats=stats)
+    assert res < g["termination_tol"], res
+    assert max(c.shape[-1] for c in x) <= 200, [c.shape for c in x]
