@@ -206,6 +206,21 @@ int ttipm_ewise(int rows, int inner, double alpha, const double* a, int64_t a_rs
  * ranks at once: out[j*256 + part] = partial || base - sum_{i>=j} Y_i ||^2, Y is (q x len). */
 int ttipm_trunc_resnorms(const double* base, const double* Y, int q, int64_t len, double* out, void* stream);
 
+/* ---- vector algebra of the host-driven LGMRES (large local blocks, ttipm_amen_host_krylov) ------------ */
+/* Number of chunks (= CTAs, <= 128) the Krylov vector kernels split a vector of nv doubles into. */
+int ttipm_cgs_parts(int64_t nv);
+/* One pass of classical Gram-Schmidt against the nvec (<= 112) basis vectors V_i = V + i*ldv (the Arnoldi step of
+ * PETSc's LGMRES behind reference cy_src/lgmres_cy.pyx:203-510): h_i = <V_i, w> (per-chunk partial sums added in a fixed
+ * order), w <- w - sum_i h_i V_i in place, h_out[0..nvec) = h, sumsq[0..parts) = partial ||w||^2 of the updated vector.
+ * partials: parts x nvec doubles of scratch. */
+int ttipm_cgs_project(const double* V, int64_t ldv, int nvec, double* w, int64_t nv, double* partials, double* h_out,
+                      double* sumsq, void* stream);
+/* out = beta * base + scale * sum_i coefs[i] * vecs[i]  (nvec <= 112 device vectors of nv doubles; vecs / coefs are HOST
+ * arrays passed by value to the kernel; base may be NULL): the solution update and the error-approximation vectors of
+ * the LGMRES cycle. */
+int ttipm_lincomb(int nvec, const double* const* vecs, const double* coefs, double scale, const double* base, double beta,
+                  double* out, int64_t nv, void* stream);
+
 /* ---- TT primitives of the IPM driver (memory bound) ---------------------------------------------- */
 /* One core of tt_add (reference cy_src/tt_ops_cy.pyx:229-258): mode 0 = first core (concatenate on the
  * last axis), 1 = middle core (block diagonal), 2 = last core (concatenate on the first axis);
@@ -239,6 +254,13 @@ int ttipm_amen_run(ttipm_amen* h, double term_tol, int r_max, double eps, int ns
                    int direction, double* final_res, int* sweeps);
 int ttipm_amen_core_shape(ttipm_amen* h, int k, int32_t* dims /* r, nb|0, n, R */);
 int ttipm_amen_get_core(ttipm_amen* h, int k, double* dst_host);
+/* Which local blocks run their Krylov solve HOST-DRIVEN (matvec through ttipm_block_matvec -- grouped contraction GEMMs
+ * over the whole machine -- plus ttipm_cgs_project / ttipm_lincomb, Hessenberg matrix on the host) instead of inside the
+ * persistent kernel of ttipm_local_lgmres: 0 = none, 1 = automatic (default: blocks whose first matvec intermediate
+ * leaves fewer than 4 output columns per shared-memory tile, i.e. left rank x operator rank large -- graphm_3 from IPM
+ * iteration 3 on), 2 = all (tests).  Same algorithm, same iteration counts.  Returns the previous mode; a negative
+ * argument only queries. */
+int ttipm_amen_host_krylov(int mode);
 /* profile != 0: time every Krylov-kernel launch of the next run() with CUDA events (read back through stats) */
 int ttipm_amen_set_profile(ttipm_amen* h, int on);
 /* Per-category profile of the last profiled run (call ttipm_amen_stats first): out[27], 3 per category =

@@ -329,6 +329,8 @@ static double amen_wall_ms() {
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+static int g_host_krylov_mode = 1;
+
 struct Amen {
     Ctx c;
     int d = 0, bs = 0;
@@ -346,6 +348,8 @@ struct Amen {
     bool direct_solve_failure = false;
     int sweeps = 0;
     long local_solves = 0, lgmres_its = 0, lgmres_matvecs = 0, lgmres_calls = 0, dense_solves = 0, krylov_failures = 0;
+    long host_krylov_solves = 0;
+    int host_krylov_mode = g_host_krylov_mode; // 0 never, 1 automatic (host_krylov_wanted), 2 always (tests)
     std::string last_krylov_error;
     std::vector<double> trace;                 // (swp, k, res_old, res_new, r*R) per local solve
     std::unique_ptr<Dense> dense;
@@ -547,6 +551,281 @@ struct Amen {
         return sol;
     }
 
+    // ---- host-driven LGMRES (same algorithm as k_lgmres; reference cy_src/lgmres_cy.pyx:203-510 over PETSc LGMRES) ---------
+    // For local blocks whose reduced-operator matvec tiles badly inside the persistent kernel (see host_krylov_wanted):
+    // the matvec goes through ttipm_block_matvec (grouped contraction GEMMs over the whole machine above its flop
+    // threshold), the vector algebra through ttipm_cgs_project / ttipm_lincomb / k_ewise, the Givens-rotated Hessenberg
+    // matrix lives on the host; one synchronising read-back per inner step.
+    struct ReducedOp {
+        Terms tA, tB;
+        Tensor inv_I, xB;
+        long r, n, R, m;
+        int nred;
+    };
+    ReducedOp reduced_op(int k, const Tensor& inv_I, long r, long n, long R) {
+        ReducedOp op;
+        op.r = r; op.n = n; op.R = R; op.m = r * n * R; op.nred = ineq ? 3 : 2;
+        op.inv_I = inv_I;
+        auto P1 = [&](Key q) -> const Tensor& { return XAX[k].at(q); };
+        auto P2 = [&](Key q) -> const Tensor& { return XAX[k + 1].at(q); };
+        auto Ak = [&](Key q) -> const Tensor& { return A.at(q)[k]; };
+        // phase A: out0 = K00 v0 + K01 v1, out1 (raw) = K01^T v0, [out2 = K31 v1 + K33 v2]
+        op.tA.add(P1({0, 0}), Ak({0, 0}), P2({0, 0}), 0, 0);
+        op.tA.add(P1({0, 1}), Ak({0, 1}), P2({0, 1}), 1, 0);
+        op.tA.add(P1({0, 1}).permute({2, 1, 0}), Ak({0, 1}).permute({0, 2, 1, 3}), P2({0, 1}).permute({2, 1, 0}), 0, 1);
+        if (ineq) {
+            op.tA.add(P1({3, 1}), Ak({3, 1}), P2({3, 1}), 1, 2);
+            op.tA.add(P1({3, 3}), Ak({3, 3}), P2({3, 3}), 2, 2);
+        }
+        // phase B on xB = [v1 ; inv_I .* out1 (+ v2)]: out1 = K21 v1 - K22 xB1
+        op.tB.add(P1({2, 1}), Ak({2, 1}), P2({2, 1}), 0, 0);
+        op.tB.add(P1({2, 2}), Ak({2, 2}), P2({2, 2}), 1, 0, -1.0);
+        op.xB = Tensor::empty(c, {2, r, n, R});
+        return op;
+    }
+    void reduced_apply(ReducedOp& op, const Tensor& src, Tensor& dst) {       // src, dst: (nred, r, n, R) contiguous
+        const long m = op.m, nR = op.n * op.R;
+        check_rc(ttipm_block_matvec(op.tA.v.data(), (int)op.tA.v.size(), (int)op.r, (int)op.R, (int)op.r, (int)op.R, (int)op.n,
+                                    op.nred, src.p, m, nR, op.R, 0, dst.p, m, nR, op.R, 0, 1.0, nullptr, 0.0, nullptr, 1, c.st),
+                 "host krylov: phase A");
+        Tensor d1 = dst.select(0, 1), s1 = src.select(0, 1), x0 = op.xB.select(0, 0), x1 = op.xB.select(0, 1);
+        ewise(c, s1, 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, &x0, nullptr);
+        if (ineq) {
+            Tensor s2 = src.select(0, 2);
+            ewise(c, d1, 1.0, nullptr, 0.0, &s2, 1.0, &op.inv_I, &x1, nullptr);
+        } else {
+            ewise(c, d1, 1.0, nullptr, 0.0, nullptr, 0.0, &op.inv_I, &x1, nullptr);
+        }
+        check_rc(ttipm_block_matvec(op.tB.v.data(), (int)op.tB.v.size(), (int)op.r, (int)op.R, (int)op.r, (int)op.R, (int)op.n, 1,
+                                    op.xB.p, m, nR, op.R, 0, dst.p + m, m, nR, op.R, 0, 1.0, nullptr, 0.0, nullptr, 1, c.st),
+                 "host krylov: phase B");
+        c.launches += 2;
+    }
+
+    Tensor host_lgmres(int k, const Tensor& inv_I, const Tensor& bvec, long r, long n, long R, int max_k, int aug_dim, int max_it,
+                       double rtol, bool apply_only, Tensor* info_out) {
+        enum { R_NONE = 0, R_RTOL = 1, R_ATOL = 2, R_ITS = 3, R_DTOL = -1, R_BREAKDOWN = -2, R_NULL = -3, R_NAN = -4 };
+        ReducedOp op = reduced_op(k, inv_I, r, n, R);
+        const long nv = (long)op.nred * op.m;
+        Tensor x = Tensor::empty(c, {(long)op.nred, r, n, R});
+        if (apply_only) {
+            reduced_apply(op, bvec, x);
+            return x;
+        }
+        const double abstol = 1e-50, dtol = 1e5, haptol = 1e-30;
+        const int ldh = max_k + 2, it_arnoldi = max_k - aug_dim, nparts = ttipm_cgs_parts(nv);
+        Tensor V = Tensor::empty(c, {(long)max_k + 2, nv});
+        Tensor AUG = Tensor::empty(c, {(long)std::max(aug_dim, 1), nv}), AAUG = Tensor::empty(c, {(long)std::max(aug_dim, 1), nv});
+        Tensor upd = Tensor::empty(c, {(long)op.nred, r, n, R});
+        Tensor partials = Tensor::empty(c, {(long)nparts, 112}), hb = Tensor::empty(c, {112 + 128});
+        auto vec = [&](const Tensor& M, long i) { return M.select(0, i).reshape({(long)op.nred, r, n, R}); };
+        auto norm_of = [&](const Tensor& v) {
+            Tensor ss;
+            ewise(c, v, 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, nullptr, &ss);
+            return sqrt(host_sums(c, {&ss})[0]);
+        };
+        auto scale_inplace = [&](Tensor v, double f) { ewise(c, v, f, nullptr, 0.0, nullptr, 0.0, nullptr, &v, nullptr); };
+        auto lincomb = [&](const std::vector<const double*>& vs, const std::vector<double>& cs, double scale, Tensor& out) {
+            check_rc(ttipm_lincomb((int)vs.size(), vs.data(), cs.data(), scale, nullptr, 0.0, out.p, nv, c.st), "lincomb");
+            c.launches++;
+        };
+        std::vector<double> hh((size_t)ldh * (max_k + 1), 0.0), hes((size_t)ldh * (max_k + 1), 0.0);
+        std::vector<double> cc(ldh, 0.0), ss(ldh, 0.0), grs(ldh, 0.0), nrs(ldh, 0.0), col(ldh, 0.0), tS(ldh, 0.0);
+        if (dev_memset(x.p, 0, sizeof(double) * (size_t)nv, c.st)) throw DriverError(92, "memset failed");
+        int its = 0, matvecs = 0, aug_ct = 0, reason = R_NONE, cycles = 0;
+        int aug_order[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        double ttol = 0.0, rnorm0 = 0.0, res = 0.0;
+        bool first = true;
+        auto converged = [&](int it, double rn) {
+            if (it == 0) {
+                ttol = std::max(rtol * rn, abstol);
+                rnorm0 = rn;
+            }
+            if (!(rn == rn) || std::isinf(rn)) return (int)R_NAN;
+            if (rn <= ttol) return rn < abstol ? (int)R_ATOL : (int)R_RTOL;
+            if (rn >= dtol * rnorm0) return (int)R_DTOL;
+            return (int)R_NONE;
+        };
+        auto aug_spot = [&](int order) {
+            for (int ii = 0; ii < aug_dim; ++ii)
+                if (aug_order[ii] == order) return ii;
+            return 0;
+        };
+        for (;;) {
+            ++cycles;
+            Tensor V0 = vec(V, 0);
+            double res_norm;
+            if (first) {
+                Tensor sq;
+                ewise(c, bvec, 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, &V0, &sq);
+                res_norm = sqrt(host_sums(c, {&sq})[0]);
+            } else {
+                reduced_apply(op, x, V0);
+                ++matvecs;
+                Tensor sq;
+                ewise(c, bvec, 1.0, &V0, -1.0, nullptr, 0.0, nullptr, &V0, &sq);
+                res_norm = sqrt(host_sums(c, {&sq})[0]);
+            }
+            first = false;
+            res = res_norm;
+            grs[0] = res_norm;
+            if (res == 0.0) {
+                reason = R_ATOL;
+                break;
+            }
+            scale_inplace(V0, 1.0 / res_norm);
+            const int it_total = it_arnoldi + aug_ct;
+            reason = converged(its, res);
+            int loc_it = 0;
+            bool hapend = false;
+            double grs_loc = res_norm;
+            while (reason == R_NONE && loc_it < it_total && its < max_it) {
+                Tensor Vn = vec(V, loc_it + 1);
+                if (loc_it < it_arnoldi) {
+                    reduced_apply(op, vec(V, loc_it), Vn);
+                    ++matvecs;
+                } else {
+                    Tensor src = vec(AAUG, aug_spot(loc_it - it_arnoldi + 1));
+                    ewise(c, src, 1.0, nullptr, 0.0, nullptr, 0.0, nullptr, &Vn, nullptr);
+                }
+                // classical Gram-Schmidt, one pass: h = V^T w, w -= V h, ||w||
+                check_rc(ttipm_cgs_project(V.p, nv, loc_it + 1, Vn.p, nv, partials.p, hb.p, hb.p + 112, c.st), "cgs_project");
+                c.launches += 2;
+                std::vector<double> hv = read_vec(c, hb);
+                double s2 = 0.0;
+                for (int g = 0; g < nparts; ++g) s2 += hv[112 + g];
+                const double tt = sqrt(s2);
+                double hapbnd = fabs(tt / grs_loc);
+                if (hapbnd > haptol) hapbnd = haptol;
+                if (tt > hapbnd) scale_inplace(Vn, 1.0 / tt);
+                else hapend = true;
+                double* hcol = hh.data() + (size_t)loc_it * ldh;
+                double* ucol = hes.data() + (size_t)loc_it * ldh;
+                for (int i = 0; i <= loc_it + 1; ++i) {
+                    const double v = i <= loc_it ? hv[i] : tt;
+                    col[i] = v;
+                    ucol[i] = v;
+                }
+                for (int j = 0; j < loc_it; ++j) {
+                    const double t0 = col[j];
+                    col[j] = cc[j] * t0 + ss[j] * col[j + 1];
+                    col[j + 1] = cc[j] * col[j + 1] - ss[j] * t0;
+                }
+                double newres = 0.0;
+                bool null_pivot = false;
+                if (!hapend) {
+                    const double t0 = sqrt(col[loc_it] * col[loc_it] + col[loc_it + 1] * col[loc_it + 1]);
+                    if (t0 == 0.0) {
+                        null_pivot = true;
+                    } else {
+                        cc[loc_it] = col[loc_it] / t0;
+                        ss[loc_it] = col[loc_it + 1] / t0;
+                        grs[loc_it + 1] = -(ss[loc_it] * grs[loc_it]);
+                        grs[loc_it] = cc[loc_it] * grs[loc_it];
+                        col[loc_it] = cc[loc_it] * col[loc_it] + ss[loc_it] * col[loc_it + 1];
+                        newres = fabs(grs[loc_it + 1]);
+                    }
+                }
+                for (int i = 0; i <= loc_it + 1; ++i) hcol[i] = col[i];
+                if (null_pivot) {
+                    reason = R_NULL;
+                    break;
+                }
+                res = newres;
+                grs_loc = grs[loc_it + 1];
+                ++loc_it;
+                ++its;
+                reason = converged(its, res);
+                if (hapend && reason == R_NONE) {
+                    reason = R_BREAKDOWN;
+                    break;
+                }
+            }
+            // solution of this cycle
+            const int it = loc_it - 1;
+            int n_arn = 0, n_aug = 0;
+            if (it >= 0) {
+                if (it_arnoldi >= it + 1) {
+                    n_arn = it + 1;
+                } else {
+                    n_arn = it_arnoldi;
+                    n_aug = it + 1 - it_arnoldi;
+                }
+                for (int i = 0; i <= it; ++i) tS[i] = grs[i];
+                for (int q = it; q >= 0; --q) {
+                    const double dgl = hh[(size_t)q * ldh + q];
+                    const double yk = (q == it && dgl == 0.0) ? 0.0 : tS[q] / dgl;
+                    nrs[q] = yk;
+                    for (int i = 0; i < q; ++i) tS[i] -= hh[(size_t)q * ldh + i] * yk;
+                }
+                std::vector<const double*> vs;
+                std::vector<double> cs;
+                for (int i = 0; i < n_arn; ++i) {
+                    vs.push_back(V.p + (long)i * nv);
+                    cs.push_back(nrs[i]);
+                }
+                for (int ii = 0; ii < n_aug; ++ii) {
+                    vs.push_back(AUG.p + (long)aug_spot(ii + 1) * nv);
+                    cs.push_back(nrs[n_arn + ii]);
+                }
+                lincomb(vs, cs, 1.0, upd);
+                ewise(c, x, 1.0, &upd, 1.0, nullptr, 0.0, nullptr, &x, nullptr);
+            }
+            // harvest the error approximation for the next cycle
+            if (reason == R_NONE && its < max_it && aug_dim > 0) {
+                int spot = 0;
+                if (aug_ct == 0) {
+                    spot = 0;
+                    ++aug_ct;
+                } else if (aug_ct < aug_dim) {
+                    spot = aug_ct;
+                    ++aug_ct;
+                } else {
+                    for (int ii = 0; ii < aug_dim; ++ii)
+                        if (aug_order[ii] == aug_dim) spot = ii;
+                }
+                const double inv = 1.0 / norm_of(upd);
+                std::vector<const double*> vs;
+                std::vector<double> cs;
+                for (int jj = 0; jj <= it_total; ++jj) {
+                    double a = 0.0;
+                    for (int ii = std::max(0, jj - 1); ii < it_total; ++ii) a += hes[(size_t)ii * ldh + jj] * nrs[ii];
+                    vs.push_back(V.p + (long)jj * nv);
+                    cs.push_back(a);
+                }
+                Tensor aug = vec(AUG, spot), aaug = vec(AAUG, spot);
+                ewise(c, upd, inv, nullptr, 0.0, nullptr, 0.0, nullptr, &aug, nullptr);
+                lincomb(vs, cs, inv, aaug);
+                for (int ii = 0; ii < aug_dim; ++ii) aug_order[ii] += 1;
+                aug_order[spot] = 1;
+            }
+            if (reason != R_NONE) break;
+            if (its >= max_it) {
+                reason = R_ITS;
+                break;
+            }
+        }
+        if (info_out) {
+            const double iv[6] = {(double)its, (double)matvecs, (double)reason, (double)cycles, res, -1.0};   // grid -1: host-driven
+            from_host(c, iv, 6, info_out->p);
+        }
+        host_krylov_solves++;
+        return x;
+    }
+
+    // The persistent kernel tiles the matvec over output columns L of the right interface and keeps the first intermediate
+    // T1 (r x Lt x n S) of a tile in shared memory: when ONE column of T1 takes most of an SM's shared memory (left rank x
+    // operator rank large: graphm_3 from IPM iteration 3 on, r ~ 60-150 with S ~ 30) it runs on R <= 16-64 CTAs that each
+    // re-read the whole left interface per column (measured: 0.6 ms per inner step at r = 130, R = 16, ~0.6 TFLOP/s).
+    bool host_krylov_wanted(long r, long n, long R, const Terms& ops, double mv_flops) const {
+        if (host_krylov_mode == 0) return false;
+        if (host_krylov_mode == 2) return true;
+        long Smax = 1;
+        for (const ttipm_term& t : ops.v) Smax = std::max<long>(Smax, std::max(t.s, t.S));
+        const double t1_col_bytes = 8.0 * (double)r * (double)(n * Smax + 4);
+        return mv_flops >= 1e8 && t1_col_bytes * 4.0 > 200.0 * 1024.0;      // fewer than 4 columns per tile
+    }
+
     void log_phase(const char* what) {             // TTIPM_AMEN_LOG: drain the stream, say which phase just finished
         if (!amen_log_on()) return;
         double probe = 0.0;
@@ -590,7 +869,17 @@ struct Amen {
             const ttipm_term* T = ops.v.data();
             const int restart = (int)std::min<long>(m, 100), aug = std::max(restart / 10, 3);
             Tensor ws = Tensor::empty(c, {(long)ttipm_lgmres_workspace(ineq, (int)r, (int)R, (int)n, restart, aug)});
+            double mvf = 0.0;
+            for (int q = 0; q < (ineq ? 6 : 4); ++q) {
+                const double s_ = (double)ops.v[q].s, S_ = (double)ops.v[q].S;
+                mvf += (q == 1 ? 2.0 : 1.0) * (2.0 * r * n * R * R * S_ + 2.0 * r * R * s_ * n * n * S_ + 2.0 * r * n * R * r * s_);
+            }
+            const bool on_host = host_krylov_wanted(r, n, R, ops, mvf);
             auto lg = [&](const Tensor& in, bool apply_only, Tensor* info) {
+                if (on_host) {
+                    ProfScope ps(c, CAT_KRYLOV, 0.0);
+                    return host_lgmres(k, inv_I, in, r, n, R, restart, aug, 300, rtol, apply_only, info);
+                }
                 Tensor out = Tensor::empty(c, {(long)nred, r, n, R});
                 ProfScope ps(c, CAT_KRYLOV, 0.0);         // work is known after the solve (inner steps): see lg_flops
                 check_rc(ttipm_local_lgmres(ineq, T + 0, T + 1, T + 2, T + 3, ineq ? T + 4 : nullptr, ineq ? T + 5 : nullptr,
@@ -1078,6 +1367,12 @@ extern "C" int ttipm_amen_run(ttipm_amen* h, double term_tol, int r_max, double 
 }
 
 // shape of solution core k: dims[0..3] = (r, nb or 0, n, R)
+extern "C" int ttipm_amen_host_krylov(int mode) {
+    const int old = g_host_krylov_mode;
+    if (mode >= 0 && mode <= 2) g_host_krylov_mode = mode;
+    return old;
+}
+
 extern "C" int ttipm_amen_set_profile(ttipm_amen* h, int on) {
     h->a.profile = on != 0;
     return 0;

@@ -81,6 +81,12 @@ SIGNATURES = {
     "ttipm_amen_get_core": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ttipm_amen_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "ttipm_amen_profile": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ttipm_amen_host_krylov": (C.c_int, [C.c_int]),
+    "ttipm_cgs_parts": (C.c_int, [C.c_int64]),
+    "ttipm_cgs_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "ttipm_lincomb": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_int64,
+                                C.c_void_p]),
     "ttipm_matvec_big_min_flops": (C.c_double, [C.c_double]),
     "ttipm_cgemm_force_ksplit": (C.c_int, [C.c_int]),
     "ttipm_cgemm_force_cfg": (C.c_int, [C.c_int]),

@@ -340,6 +340,28 @@ def case_elementwise(rt):
     part = rt.to_host(K.trunc_resnorms(rt.to_device(base), rt.to_device(Y), rt=rt)).sum(axis=1)
     want = np.array([np.sum((base - Y[j:].sum(axis=0)) ** 2) for j in range(5)])
     errs["trunc_resnorms"] = rel(part, want)
+    # vector kernels of the host-driven LGMRES (csrc/krylov_ops.cu): one classical Gram-Schmidt pass, linear combinations
+    import ctypes as C
+    nv, nvec = 1531, 7
+    Vh = np.linalg.qr(rng.standard_normal((nv, nvec)))[0].T.copy()
+    wh = rng.standard_normal(nv)
+    Vd, wd = rt.to_device(Vh), rt.to_device(wh)
+    parts = int(rt.lib.ttipm_cgs_parts(nv))
+    scratch, hb = rt.empty(parts * 112), rt.empty(112 + 128)
+    rt.check(rt.lib.ttipm_cgs_project(K._ptr(Vd), nv, nvec, K._ptr(wd), nv, K._ptr(scratch), K._ptr(hb),
+                                      C.c_void_p(hb.data_ptr() + 112 * 8), rt.stream()), "cgs_project")
+    hv = rt.to_host(hb)
+    h_ref = Vh @ wh
+    w_ref = wh - Vh.T @ h_ref
+    errs["cgs_h"] = rel(hv[:nvec], h_ref)
+    errs["cgs_w"] = rel(rt.to_host(wd), w_ref)
+    errs["cgs_norm"] = rel(np.sqrt(hv[112:112 + parts].sum()), np.linalg.norm(w_ref))
+    coefs = rng.standard_normal(nvec)
+    ptrs = (C.c_void_p * nvec)(*[Vd.data_ptr() + 8 * nv * i for i in range(nvec)])
+    cf = (C.c_double * nvec)(*coefs)
+    out = rt.empty(nv)
+    rt.check(rt.lib.ttipm_lincomb(nvec, ptrs, cf, 0.5, K._ptr(wd), -2.0, K._ptr(out), nv, rt.stream()), "lincomb")
+    errs["lincomb"] = rel(rt.to_host(out), 0.5 * (coefs @ Vh) - 2.0 * w_ref)
     return errs
 
 

@@ -216,6 +216,35 @@ def test_restarted_amen_vs_reference_output_gpu(path):
     _restarted_vs_reference(rt_util.cuda_runtime(), path)
 
 
+def _with_host_krylov(rt, fn):
+    """run fn() with EVERY Krylov solve of the native driver host-driven (ttipm_amen_host_krylov(2)): block matvec through
+    ttipm_block_matvec, Gram-Schmidt / combinations through csrc/krylov_ops.cu, Hessenberg matrix on the host"""
+    old = rt.lib.ttipm_amen_host_krylov(2)
+    try:
+        return fn()
+    finally:
+        rt.lib.ttipm_amen_host_krylov(old)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", WITH_REF_OUTPUT, ids=os.path.basename)
+def test_restarted_amen_host_krylov_vs_reference_output_gpu(path):
+    """The host-driven LGMRES (large local blocks; forced for every block here) against the REFERENCE's stored outputs:
+    same ranks, same solution, same residual before / after every local solve as the PETSc-backed reference run."""
+    rt = rt_util.cuda_runtime()
+    _with_host_krylov(rt, lambda: _restarted_vs_reference(rt, path))
+
+
+def test_block_amen_host_krylov_vs_oracle_emu():
+    """CPU tier of the same: an inequality system whose local solves are Krylov solves, kernels on the emulator."""
+    rt = rt_util.emu_runtime()
+    out = _with_host_krylov(rt, lambda: AC.run_block_amen(rt, G.amen_files("amen_corr_clust_8_r1_s208_7*")[0],
+                                                          use_oracle=True, native=True))
+    assert out["sweeps_dev"] == out["sweeps_oracle"] and out["solves_dev"] == out["solves_oracle"], out
+    assert out["ranks_dev"] == out["ranks_oracle"], out
+    assert out["trace_absdiff"] < 1e-9 and out["sol_rel_diff"] < 1e-6, out
+
+
 @pytest.mark.gpu
 def test_restart_ladder_gpu():
     _restart_ladder(rt_util.cuda_runtime())

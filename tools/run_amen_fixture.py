@@ -23,6 +23,11 @@ def main():
     path = sys.argv[1]
     g = G.load_amen(path)
     rt = get_runtime()
+    for a in sys.argv[2:]:
+        if a.startswith("--big-min-flops="):      # flop threshold of the grouped-GEMM form of the block matvec
+            rt.lib.ttipm_matvec_big_min_flops(float(a.split("=")[1]))
+        if a.startswith("--host-krylov="):       # 0 never, 1 automatic (default), 2 always
+            rt.lib.ttipm_amen_host_krylov(int(a.split("=")[1]))
     print(json.dumps(dict(file=os.path.basename(path), d=g["d"], ineq=g["ineq"], rank_restriction=g["rank_restriction"],
                           termination_tol=g["termination_tol"], eps=g["eps"], inner_m=g["inner_m"],
                           op_ranks={f"{k[0]}{k[1]}": max(c.shape[0] for c in v) for k, v in g["A"].items()},
