@@ -146,6 +146,8 @@ TT_GLOBAL void k_sumsq_strided(const SumsqParams p) {
 
 using namespace ttipm;
 
+static double g_starved_min_flops = 5e7;
+
 extern "C" int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, int L, int r, int R, int nmode,
                                   int nb_out, const double* x, int64_t x_block_stride, int64_t x_row_stride,
                                   int64_t x_mode_stride, int64_t x_batch_stride, double* y, int64_t y_block_stride,
@@ -193,6 +195,21 @@ extern "C" int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, in
         }
         return fail(4, "block_matvec: shape l=%d L=%d r=%d R=%d s=%d S=%d needs %d B shared memory (> %d)", l, L, r,
                     R, smax, Smax, p.g.smem_bytes, di.smem_optin);
+    }
+    {
+        // A starved fused launch: the fused kernel owns (output block, L-tile) items, so a block with few output columns
+        // (tall-left local blocks of graphm_3: l = 130-190 next to L = 16) runs on a handful of CTAs that each stream the
+        // whole left interface.  From 5e7 flop on the three machine-wide launches of the grouped form are faster there
+        // (measured on B200, 300 Krylov steps at (l, L) = (130, 16): 80.7 -> 61.0 ms; blocks with L >= 64 keep the fused form).
+        double flops = 0.0;
+        for (int q = 0; q < nterms; ++q)
+            flops += 2.0 * r * nmode * R * L * p.t[q].S + 2.0 * r * L * p.t[q].s * nmode * nmode * p.t[q].S +
+                     2.0 * l * nmode * L * r * p.t[q].s;
+        if ((long)nb_out * p.g.ntiles * nbatch * 3 < di.sms && flops * nbatch >= g_starved_min_flops &&
+            mv_big_possible(nterms, l, L, nmode, nb_out, sumsq != nullptr))
+            return mv_big(p.t, nterms, l, L, r, R, nmode, nb_out, x, x_block_stride, x_row_stride, x_mode_stride,
+                          x_batch_stride, y, y_block_stride, y_row_stride, y_mode_stride, y_batch_stride, y_scale, sub,
+                          sub_scale, sumsq, nbatch, (tt_stream_t)stream);
     }
     p.x = x; p.x_bs = x_block_stride; p.x_rs = x_row_stride; p.x_ns = x_mode_stride; p.x_batch = x_batch_stride;
     p.y = y; p.y_bs = y_block_stride; p.y_rs = y_row_stride; p.y_ns = y_mode_stride; p.y_batch = y_batch_stride;
