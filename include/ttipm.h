@@ -104,7 +104,9 @@ int ttipm_phi_update(const ttipm_phi_term* terms, int nterms, int forward, const
 /* K3 -- right-hand-side contractions (reference src/tt_als.py:82, :260-265, src/tt_ipm.py:187-189)
  *   mode 0: out[r,n,R] = sum Xb1[b,r] B[b,n,B'] Xb2[B',R]      (projection; out has row stride out_row_stride)
  *   mode 1: out[B',R]  = sum Xb1[b,r] B[b,n,B'] core[r,n,R]    (forward interface)
- *   mode 2: out[b,r]   = sum Xb2[B',R] B[b,n,B'] core[r,n,R]   (backward interface) */
+ *   mode 2: out[b,r]   = sum Xb2[B',R] B[b,n,B'] core[r,n,R]   (backward interface)
+ * In mode 0 a term with B == NULL is a "zero term": its out block (r x n x R, row stride out_row_stride) is cleared by
+ * the kernel (blocks of the local right-hand side without a core; saves a memset node in the launch chain). */
 typedef struct ttipm_rhs_term {
     const double* Xb1;  /* (b, r)  or NULL when unused */
     const double* B;    /* (b, n, B') */

@@ -105,8 +105,10 @@ static inline std::vector<Tensor> phi_update(Ctx& c, const std::vector<Tensor>& 
 static inline Tensor rhs_project(Ctx& c, const std::vector<Tensor>& X1, const std::vector<Tensor>& Bc,
                           const std::vector<Tensor>& X2, const std::vector<int>& rows, long r, int nb, long n, long R) {
     Tensor out = Tensor::empty(c, {r, (long)nb, n, R});
-    if (dev_memset(out.p, 0, sizeof(double) * (size_t)out.numel(), c.st)) throw DriverError(92, "memset failed");
-    if (rows.empty()) return out;
+    if (rows.empty()) {
+        if (dev_memset(out.p, 0, sizeof(double) * (size_t)out.numel(), c.st)) throw DriverError(92, "memset failed");
+        return out;
+    }
     std::vector<ttipm_rhs_term> t(rows.size());
     for (size_t q = 0; q < rows.size(); ++q) {
         t[q].Xb1 = X1[q].p; t[q].B = Bc[q].p; t[q].Xb2 = X2[q].p;
@@ -116,6 +118,15 @@ static inline Tensor rhs_project(Ctx& c, const std::vector<Tensor>& X1, const st
     double work = 0.0;
     for (size_t q = 0; q < rows.size(); ++q)
         work += 2.0 * t[q].b * r * n * t[q].Bp + 2.0 * r * n * t[q].Bp * R;
+    // blocks without a right-hand-side core: "zero terms" (B == NULL), cleared by the kernel itself
+    for (int j = 0; j < nb; ++j) {
+        bool has = false;
+        for (int row : rows) has = has || row == j;
+        if (has) continue;
+        ttipm_rhs_term z;
+        z.Xb1 = nullptr; z.B = nullptr; z.Xb2 = nullptr; z.out = out.p + j * out.s[1]; z.b = 0; z.Bp = 0;
+        t.push_back(z);
+    }
     ProfScope ps(c, CAT_RHS, work);
     check_rc(ttipm_rhs_contract(t.data(), (int)t.size(), 0, nullptr, (int)r, (int)R, (int)n, out.s[0], c.st), "rhs_project");
     c.launches++;

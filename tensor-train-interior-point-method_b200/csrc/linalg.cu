@@ -745,6 +745,12 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
     const long long t_start = lin_now();
     long long tm[4] = {0, 0, 0, 0};
     if (threadIdx.x == 0) mbar_init(c.mbar, 1);
+    // the sweep flags are zeroed here instead of by a memset node ahead of the launch (a memset between two kernels breaks
+    // the programmatic dependent launch chain); they are first read after several phase barriers.  The atomic grid barrier's
+    // counter (flags + 64 .. 79, cooperative non-cluster launches only) is still cleared by the host.
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < 2 * TT_LIN_HDR; i += blockDim.x)
+            if (i < 64 || i >= 80) flags[i] = 0;
     __syncthreads();
 
     // working copy, column-major: A (M x N), or A^T (N x M) for a wide SVD
@@ -890,6 +896,7 @@ struct LinPlan {
     int threads;
     long smem_bytes;
     long ws_total;
+    double* ws;
 };
 
 static long even_up(long v) { return v + (v & 1); }
@@ -1007,8 +1014,10 @@ static int lin_launch_t(LinPlan& pl, int nbatch, tt_stream_t st) {
         if (G > per_sm * di.sms) G = per_sm * di.sms;
     }
 #endif
-    if (G > 1)
+    if (G > 1) {
+        if (dev_memset(pl.ws, 0, (size_t)nbatch * TT_LIN_HDR * 8, st)) return fail(5, "linalg: memset failed");
         return launch_kernel("k_linalg", k_linalg<NT>, dim3(G, nbatch), dim3(pl.threads), (size_t)pl.smem_bytes, st, true, p);
+    }
     return launch_kernel("k_linalg", k_linalg<NT>, dim3(1, nbatch), dim3(pl.threads), (size_t)pl.smem_bytes, st, false, p);
 }
 
@@ -1021,7 +1030,7 @@ static int lin_launch(int mode, const double* A, long a_rs, long a_cs, long a_bs
     p.A = A; p.a_rs = a_rs; p.a_cs = a_cs; p.a_bs = a_bs;
     p.U = U; p.S = S; p.Wt = Wt; p.info = info; p.ws = ws;
     if (((uintptr_t)ws & 15) != 0) return fail(1, "linalg: workspace must be 16-byte aligned");
-    if (dev_memset(ws, 0, (size_t)nbatch * TT_LIN_HDR * 8, st)) return fail(5, "linalg: memset failed");
+    pl.ws = ws;
     if (pl.threads == 384) return lin_launch_t<384>(pl, nbatch, st);
     return lin_launch_t<512>(pl, nbatch, st);
 }

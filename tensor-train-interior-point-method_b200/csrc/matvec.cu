@@ -50,7 +50,11 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_block_matvec(const MvParams p
         double* scratch = smem + g.oOffs;   // offs are dead here
         __syncthreads();
         const double tot = block_sum(ss, scratch);
-        if (threadIdx.x == 0) p.sumsq[(long)batch * p.nb_out * g.L + out_blk * g.L + tile] = tot;
+        double* slots = p.sumsq + (long)batch * p.nb_out * g.L + out_blk * g.L;
+        if (threadIdx.x == 0) slots[tile] = tot;
+        // slots beyond the tile count (L per output block) are cleared by the last tile instead of a memset node
+        if (tile == g.ntiles - 1)
+            for (int i = g.ntiles + threadIdx.x; i < g.L; i += blockDim.x) slots[i] = 0.0;
     }
 }
 
@@ -168,15 +172,21 @@ extern "C" int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, in
     p.nterms = nterms;
     if (!fits_int(x_row_stride) || !fits_int(x_mode_stride) || !fits_int(y_row_stride) || !fits_int(y_mode_stride))
         return fail(1, "block_matvec: x / y strides too large");
-    if (sumsq && dev_memset(sumsq, 0, sizeof(double) * (size_t)nbatch * nb_out * L, (tt_stream_t)stream))
-        return fail(5, "memset failed");
+    // the grouped-GEMM form writes one sum-of-squares slot per output tile: the others are cleared up front (the fused
+    // kernel clears its unused slots itself -- no memset node in the launch chain of the common case)
+    auto clear_sumsq = [&]() {
+        return sumsq && dev_memset(sumsq, 0, sizeof(double) * (size_t)nbatch * nb_out * L, (tt_stream_t)stream);
+    };
     // large local blocks: every stage of the chain is a machine-filling GEMM (cgemm.cu)
-    if (mv_big_wanted(p.t, nterms, l, L, r, R, nmode, nb_out, nbatch))
+    if (mv_big_wanted(p.t, nterms, l, L, r, R, nmode, nb_out, nbatch)) {
+        if (clear_sumsq()) return fail(5, "memset failed");
         return mv_big(p.t, nterms, l, L, r, R, nmode, nb_out, x, x_block_stride, x_row_stride, x_mode_stride, x_batch_stride,
                       y, y_block_stride, y_row_stride, y_mode_stride, y_batch_stride, y_scale, sub, sub_scale, sumsq, nbatch,
                       (tt_stream_t)stream);
+    }
     DevInfo di = dev_info();
     if (mv_plan(p.g, l, L, r, R, nmode, smax, Smax, nb_out, (di.sms * 2 + nbatch - 1) / nbatch, di.smem_optin)) {
+        if (clear_sumsq()) return fail(5, "memset failed");
         // the fused kernel's intermediates do not fit shared memory: the grouped-GEMM path has no such limit
         if (mv_big_possible(nterms, l, L, nmode, nb_out, sumsq != nullptr))
             return mv_big(p.t, nterms, l, L, r, R, nmode, nb_out, x, x_block_stride, x_row_stride, x_mode_stride,
@@ -206,10 +216,12 @@ extern "C" int ttipm_block_matvec(const ttipm_term* terms, int nterms, int l, in
             flops += 2.0 * r * nmode * R * L * p.t[q].S + 2.0 * r * L * p.t[q].s * nmode * nmode * p.t[q].S +
                      2.0 * l * nmode * L * r * p.t[q].s;
         if ((long)nb_out * p.g.ntiles * nbatch * 3 < di.sms && flops * nbatch >= g_starved_min_flops &&
-            mv_big_possible(nterms, l, L, nmode, nb_out, sumsq != nullptr))
+            mv_big_possible(nterms, l, L, nmode, nb_out, sumsq != nullptr)) {
+            if (clear_sumsq()) return fail(5, "memset failed");
             return mv_big(p.t, nterms, l, L, r, R, nmode, nb_out, x, x_block_stride, x_row_stride, x_mode_stride,
                           x_batch_stride, y, y_block_stride, y_row_stride, y_mode_stride, y_batch_stride, y_scale, sub,
                           sub_scale, sumsq, nbatch, (tt_stream_t)stream);
+        }
     }
     p.x = x; p.x_bs = x_block_stride; p.x_rs = x_row_stride; p.x_ns = x_mode_stride; p.x_batch = x_batch_stride;
     p.y = y; p.y_bs = y_block_stride; p.y_rs = y_row_stride; p.y_ns = y_mode_stride; p.y_batch = y_batch_stride;

@@ -130,6 +130,13 @@ TT_GLOBAL void __launch_bounds__(TT_MAX_THREADS) k_rhs_contract(const RhsParams 
     if (p.mode == 0) {
         // rows rho in [r0, r0+rt): T[(rho,n),B'] = sum_b Xb1[b,rho] B[b,(n,B')] ; out[(rho,n),R] = T Xb2
         const int r0 = tl * p.tile, rt = imin(p.tile, r - r0);
+        if (!t.B) {
+            // "zero term": this output block has no right-hand-side core -- cleared here instead of by a memset node ahead of
+            // the launch (a memset between two kernels breaks the programmatic dependent launch chain)
+            for (int i = threadIdx.x; i < rt * nm * R; i += blockDim.x)
+                t.out[(long)(r0 + i / (nm * R)) * p.out_rs + i % (nm * R)] = 0.0;
+            return;
+        }
         for (int i = threadIdx.x; i < rt * nm * Bp; i += blockDim.x) {
             const int bp = i % Bp, n = (i / Bp) % nm, rho = i / (Bp * nm);
             double acc = 0.0;
@@ -279,6 +286,11 @@ extern "C" int ttipm_rhs_contract(const ttipm_rhs_term* terms, int nterms, int m
     for (int i = 0; i < nterms; ++i) {
         p.t[i].Xb1 = terms[i].Xb1; p.t[i].B = terms[i].B; p.t[i].Xb2 = terms[i].Xb2; p.t[i].out = terms[i].out;
         p.t[i].b = terms[i].b; p.t[i].Bp = terms[i].Bp;
+        if (!terms[i].B) {
+            if (mode != 0) return fail(1, "rhs_contract: zero terms (B == NULL) exist in mode 0 only");
+            p.t[i].b = 0; p.t[i].Bp = 0;
+            continue;
+        }
         bmax = imax(bmax, terms[i].b); Bmax = imax(Bmax, terms[i].Bp);
     }
     p.core = core; p.r = r; p.R = R; p.nm = nmode; p.mode = mode; p.out_rs = out_row_stride;
