@@ -298,6 +298,13 @@ int ttipm_tt_round(ttipm_tt* h, double eps, int collect, double* dropped);
 ttipm_tt* ttipm_tt_add(const ttipm_tt* a, const ttipm_tt* b);
 /* tt_inner_prod (cy_src/tt_ops_cy.pyx:506-520) */
 int ttipm_tt_inner(ttipm_tt* a, const ttipm_tt* b, double* out);
+/* Fused inner-product chain <a, b> of two trains given as device core pointers (host arrays of d pointers; core k of a
+ * is (ra[k], nm[k], ra[k+1]) contiguous, of b (rb[k], nm[k], rb[k+1]); boundary ranks 1): ONE single-CTA launch that keeps
+ * the running (R1 x R2) matrix and the intermediate of reference cy_src/tt_ops_cy.pyx:506-520 in shared memory, out = one
+ * device double.  Returns 0, an error code (> 0), or -1 when the chain does not fit the kernel (more than 40 cores, or a
+ * per-core intermediate above 2048 doubles, where two GEMM launches per core are faster: ttipm_tt_inner then runs those). */
+int ttipm_tt_inner_chain(int d, const double* const* a, const double* const* b, const int32_t* ra, const int32_t* rb,
+                         const int32_t* nm, double* out, void* stream);
 /* zip-up products with swap_cores (cy_src/tt_ops_cy.pyx:393-502): kind 0 tt_fast_matrix_vec_mul(A, B),
  * 1 tt_fast_mat_mat_mul(A, B), 2 tt_fast_hadamard(A, B); eps as passed to the reference function; NULL on failure */
 ttipm_tt* ttipm_tt_zipup(int kind, const ttipm_tt* A, const ttipm_tt* B, double eps);

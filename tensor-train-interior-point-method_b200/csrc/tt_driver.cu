@@ -199,6 +199,34 @@ static void add(TT& out, const TT& a, const TT& b) {
 
 // cy_src/tt_ops_cy.pyx:506-520
 static double inner(Ctx& c, const TT& a, const TT& b) {
+    {   // one launch for the whole chain while the running matrix and the intermediate fit one CTA's shared memory
+        const int d = (int)a.cores.size();
+        if (d >= 1 && d == (int)b.cores.size() && d <= 40) {
+            std::vector<const double*> pa(d), pb(d);
+            std::vector<int32_t> ra(d + 1), rb(d + 1), nm(d);
+            bool ok = true;
+            for (int k = 0; k < d; ++k) {
+                const Core& c1 = a.cores[k];
+                const Core& c2 = b.cores[k];
+                if (c2.nm() != c1.nm()) throw DriverError(1, "tt_inner_prod: mode sizes differ");
+                ok = ok && c1.t.contiguous() && c2.t.contiguous();
+                pa[k] = c1.t.p; pb[k] = c2.t.p;
+                ra[k] = (int32_t)c1.r; rb[k] = (int32_t)c2.r; nm[k] = (int32_t)c1.nm();
+                ra[k + 1] = (int32_t)c1.R; rb[k + 1] = (int32_t)c2.R;
+            }
+            if (ok && ra[0] == 1 && rb[0] == 1 && ra[d] == 1 && rb[d] == 1) {
+                Tensor out = Tensor::empty(c, {1});
+                const int rc = ttipm_tt_inner_chain(d, pa.data(), pb.data(), ra.data(), rb.data(), nm.data(), out.p, c.st);
+                if (rc == 0) {
+                    c.launches++;
+                    double v = 0.0;
+                    to_host(c, out.p, 1, &v);
+                    return v;
+                }
+                if (rc > 0) check_rc(rc, "tt_inner_chain");
+            }
+        }
+    }
     Tensor res = Tensor::empty(c, {1, 1});
     const double one = 1.0;
     from_host(c, &one, 1, res.p);

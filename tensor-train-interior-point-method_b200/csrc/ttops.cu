@@ -150,3 +150,89 @@ extern "C" int ttipm_scale2d(const double* in, int64_t in_rs, int64_t in_cs, int
     return launch_kernel("k_scale2d", k_scale2d, dim3(grid_for((long)rows * cols)), dim3(block_threads()), 0,
                          (tt_stream_t)stream, false, p);
 }
+
+// ---------------------------------------------------------------------------------------
+// Fused inner-product chain <a, b> of two tensor trains (reference cy_src/tt_ops_cy.pyx:506-520): the running
+// (R1 x R2) matrix and the intermediate T stay in shared memory of ONE CTA for the whole chain -- one launch instead of
+// two GEMM launches per core.  Per core, in the reference's order:
+//   T[j, (n, b)]  = sum_i res[i, j] c1[i, n, b]          (tensordot(result, core1, axes = ([0], [0])))
+//   res'[b, e]    = sum_(j, n) T[j, (n, b)] c2[j, n, e]  (tensordot(temp, core2, axes = ([0, 1], [0, 1])))
+// Used for small trains (intermediate of a core <= 2048 doubles: bond ranks up to ~20 at mode size 4, ~11 at mode size
+// 16); larger trains keep the GEMM chain, which is faster there.
+namespace ttipm {
+
+#define TT_INNER_MAX_CORES 40
+struct InnerParams {
+    const double* a[TT_INNER_MAX_CORES];
+    const double* b[TT_INNER_MAX_CORES];
+    int ra[TT_INNER_MAX_CORES + 1], rb[TT_INNER_MAX_CORES + 1], nm[TT_INNER_MAX_CORES];
+    int d;
+    int oT;              // offset of T behind the two res buffers (doubles)
+    int res_cap;         // doubles per res buffer
+    double* out;
+};
+TT_GLOBAL void k_tt_inner(const InnerParams p) {
+    pdl_entry();
+    TT_SMEM_DECL(smem_raw);
+    double* smem = (double*)smem_raw;
+    double* res = smem;
+    double* nxt = smem + p.res_cap;
+    double* T = smem + p.oT;
+    if (threadIdx.x == 0) res[0] = 1.0;
+    __syncthreads();
+    for (int k = 0; k < p.d; ++k) {
+        const int r1 = p.ra[k], R1 = p.ra[k + 1], r2 = p.rb[k], R2 = p.rb[k + 1], nn = p.nm[k];
+        const double* c1 = p.a[k];
+        const double* c2 = p.b[k];
+        const int nT = r2 * nn * R1;
+        for (int o = threadIdx.x; o < nT; o += blockDim.x) {
+            const int j = o / (nn * R1), q = o % (nn * R1);            // q = (n, b)
+            double acc = 0.0;
+            for (int i = 0; i < r1; ++i) acc += res[i * r2 + j] * c1[(long)i * nn * R1 + q];
+            T[o] = acc;
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < R1 * R2; o += blockDim.x) {
+            const int bb = o / R2, e = o % R2;
+            double acc = 0.0;
+            for (int j = 0; j < r2; ++j)
+                for (int n = 0; n < nn; ++n)
+                    acc += T[(j * nn + n) * R1 + bb] * c2[((long)j * nn + n) * R2 + e];
+            nxt[o] = acc;
+        }
+        __syncthreads();
+        double* t = res;
+        res = nxt;
+        nxt = t;
+    }
+    if (threadIdx.x == 0) p.out[0] = res[0];
+}
+
+}  // namespace ttipm
+
+// a[k]: (ra[k], nm[k], ra[k+1]) contiguous device cores, b[k] likewise; out: one device double.
+// Returns 0, an error code, or -1 when the chain does not fit the kernel (caller falls back to the GEMM chain).
+extern "C" int ttipm_tt_inner_chain(int d, const double* const* a, const double* const* b, const int32_t* ra,
+                                    const int32_t* rb, const int32_t* nm, double* out, void* stream) {
+    using namespace ttipm;
+    if (d < 1) return fail(1, "tt_inner_chain: empty train");
+    if (d > TT_INNER_MAX_CORES) return -1;
+    InnerParams p;
+    long res_cap = 1, t_cap = 1;
+    for (int k = 0; k < d; ++k) {
+        p.a[k] = a[k]; p.b[k] = b[k]; p.ra[k] = ra[k]; p.rb[k] = rb[k]; p.nm[k] = nm[k];
+        res_cap = std::max<long>(res_cap, (long)ra[k + 1] * rb[k + 1]);
+        t_cap = std::max<long>(t_cap, (long)rb[k] * nm[k] * ra[k + 1]);
+    }
+    p.ra[d] = ra[d]; p.rb[d] = rb[d];
+    if (ra[0] != 1 || rb[0] != 1 || ra[d] != 1 || rb[d] != 1) return fail(1, "tt_inner_chain: boundary ranks must be 1");
+    res_cap += res_cap & 1;
+    const long bytes = (2 * res_cap + t_cap + 2) * 8;
+    DevInfo di = dev_info();
+    // one CTA runs the chain as dependent FMA loops: measured on B200 (tools/bench_inner.py) 36 us per call at d = 5, bond rank 8
+    // (~100 us as a GEMM chain) but 909 us at d = 13, bond rank 32 (intermediate of 4096 doubles per core) against ~250 us for
+    // the GEMM chain -- the fused form is for the small trains of the IPM iterates only
+    if (bytes > di.smem_optin - 1024 || t_cap > 2048) return -1;
+    p.d = d; p.res_cap = (int)res_cap; p.oT = (int)(2 * res_cap); p.out = out;
+    return launch_kernel("k_tt_inner", k_tt_inner, dim3(1), dim3(block_threads()), (size_t)bytes, (tt_stream_t)stream, false, p);
+}

@@ -109,6 +109,8 @@ SIGNATURES = {
     "ttipm_tt_round": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     "ttipm_tt_add": (C.c_void_p, [C.c_void_p, C.c_void_p]),
     "ttipm_tt_inner": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
+    "ttipm_tt_inner_chain": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "ttipm_tt_zipup": (C.c_void_p, [C.c_int, C.c_void_p, C.c_void_p, C.c_double]),
     "ttipm_tt_reshape": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
     "ttipm_tt_transpose": (C.c_void_p, [C.c_void_p]),

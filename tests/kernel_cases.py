@@ -401,6 +401,16 @@ def case_tt_algebra(rt):
         errs["inner4"] = abs(T.tt_inner_prod(a4, b4) - float(z["tt/inner4"])) / abs(float(z["tt/inner4"]))
         errs["inner3"] = abs(T.tt_inner_prod(a3, b3) - float(z["tt/inner3"])) / abs(float(z["tt/inner3"]))
         errs["norm3"] = abs(T.tt_norm(a3) - float(z["tt/norm3"])) / float(z["tt/norm3"])
+        # the fused single-launch chain (small ranks, above) and the GEMM chain it falls back to when the intermediate
+        # of a core is beyond the fused kernel's size limit (ranks 70 at mode size 16), both against NumPy
+        rngi = np.random.default_rng(3)
+        for tag, rk, nn in (("inner_fused", 9, 4), ("inner_gemm_chain", 70, 16)):
+            ta = [rngi.standard_normal(sh) / np.sqrt(sh[0] * sh[1]) for sh in ((1, nn, rk), (rk, nn, rk), (rk, nn, 1))]
+            tb = [rngi.standard_normal(sh) / np.sqrt(sh[0] * sh[1]) for sh in ((1, nn, rk + 1), (rk + 1, nn, rk), (rk, nn, 1))]
+            want = np.array([[1.0]])
+            for c1, c2 in zip(ta, tb):
+                want = np.tensordot(np.tensordot(want, c1, axes=([0], [0])), c2, axes=([0, 1], [0, 1]))
+            errs[tag] = abs(T.tt_inner_prod(ta, tb) - want[0, 0]) / abs(want[0, 0])
         errs["esum4"] = abs(T.tt_entrywise_sum(a4) - float(z["tt/esum4"])) / abs(float(z["tt/esum4"]))
         cmp("hadamard4", T.tt_fast_hadamard(cp(a4), cp(b4), 1e-12), zipup=True)
         cmp("hadamard3", T.tt_fast_hadamard(cp(a3), cp(b3), 1e-12), zipup=True)
