@@ -123,6 +123,10 @@ int ttipm_gemm(int M, int N, int K, double alpha, const double* A, int64_t a_rs,
                const double* B, int64_t b_rs, int64_t b_cs, int64_t b_bs, double beta, double* C, int64_t c_rs,
                int64_t c_cs, int64_t c_bs, int nbatch, void* stream);
 
+/* Planning only, no device access: grid (CTAs) and dynamic shared memory (bytes) ttipm_local_lgmres would launch with for a
+ * local block (r, nmode, R) whose operator cores all have rank op_rank; 0, or the error ttipm_local_lgmres would return
+ * (4: the block does not fit the kernel).  The CPU-tier tests pin the set-up's grid search with it. */
+int ttipm_lgmres_plan(int ineq, int r, int R, int nmode, int op_rank, int restart, int* grid, int* smem_bytes);
 /* Device-resident LGMRES(restart, augment) on the Schur-reduced local KKT operator
  *   eq   (ineq=0): [y; x]    -> [K00 y + K01 x ; K21 x - K22 (inv_I o K01^T y)]
  *   ineq (ineq=1): [y; x; t] -> [K00 y + K01 x ; K21 x - K22 (inv_I o K01^T y + t) ; K31 x + K33 t]

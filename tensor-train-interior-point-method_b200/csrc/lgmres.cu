@@ -687,6 +687,28 @@ static int launch_info_copy(const int* ci, const double* cd, double* out, int gr
 
 using namespace ttipm;
 
+// planning only: what ttipm_local_lgmres would launch for a block of this shape whose operator cores all have rank
+// op_rank (no device access; the CPU tier pins the grid search against cycling with it)
+extern "C" int ttipm_lgmres_plan(int ineq, int r, int R, int nmode, int op_rank, int restart, int* grid, int* smem_bytes) {
+    if (r < 1 || R < 1 || nmode < 1 || op_rank < 1 || restart < 2) return fail(1, "lgmres_plan: bad arguments");
+    ttipm_term t;
+    memset(&t, 0, sizeof(t));
+    t.s = op_rank; t.S = op_rank;
+    t.p1_strides[0] = (int64_t)op_rank * r; t.p1_strides[1] = r; t.p1_strides[2] = 1;
+    t.a_strides[0] = (int64_t)nmode * nmode * op_rank; t.a_strides[1] = (int64_t)nmode * op_rank; t.a_strides[2] = op_rank;
+    t.a_strides[3] = 1;
+    t.p2_strides[0] = (int64_t)op_rank * R; t.p2_strides[1] = R; t.p2_strides[2] = 1;
+    t.alpha = 1.0;
+    LgParams p;
+    int G = 1, smem = 0;
+    int rc = lg_setup(p, ineq, &t, &t, &t, &t, ineq ? &t : nullptr, ineq ? &t : nullptr, nullptr, r, R, nmode, 0, &G, &smem,
+                      restart);
+    if (rc) return rc;
+    if (grid) *grid = G;
+    if (smem_bytes) *smem_bytes = smem;
+    return 0;
+}
+
 extern "C" int64_t ttipm_lgmres_workspace(int ineq, int r, int R, int nmode, int restart, int augment) {
     const int64_t nv = (int64_t)(ineq ? 3 : 2) * r * nmode * R, m = (int64_t)r * nmode * R;
     const int64_t mk = restart;

@@ -82,6 +82,8 @@ SIGNATURES = {
     "ttipm_amen_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "ttipm_amen_profile": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ttipm_amen_host_krylov": (C.c_int, [C.c_int]),
+    "ttipm_lgmres_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int)]),
     "ttipm_cgs_parts": (C.c_int, [C.c_int64]),
     "ttipm_cgs_project": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),

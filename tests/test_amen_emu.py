@@ -1,5 +1,6 @@
 """CPU tier: the whole hot path (native C++ sweep driver + the real kernel sources under -DTTIPM_EMU) on the
 smallest traced KKT systems vs the oracle, and the host mirror's containers / dispatch logic."""
+import os
 import numpy as np
 import pytest
 
@@ -120,3 +121,33 @@ def test_dropin_rebinds_only_hot_path_names():
         assert dropin.install(prefixes=("refproblem_",)).get("refproblem_fake") is None       # idempotent
     finally:
         del sys.modules["refproblem_fake"]
+
+
+def test_krylov_setup_grid_search_terminates():
+    """lg_setup's grid search on a 148-SM device (TTIPM_EMU_SMS=148 in a fresh process; planning needs no device): before the
+    fix of round 2 / session 3 a matvec plan that filled the shared memory to the last KB made the search alternate between
+    G = items and 2 G forever on the HOST -- graphm_3, IPM iteration 4, local block (r, R) = (150, 16), operator ranks 30,
+    restart 100.  Every shape of that solve (and a few around it) must come back at once with a plan inside the 227 KB or
+    with error 4."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, os, sys
+sys.path[:0] = [os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "tensor-train-interior-point-method_b200")]
+import build_emu
+lib = C.CDLL(build_emu.build())
+lib.ttipm_lgmres_plan.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_int)] * 2
+for ineq in (0, 1):
+    for (r, R, s) in ((150, 16, 30), (130, 16, 30), (188, 16, 30), (61, 64, 36), (16, 125, 30), (100, 108, 5), (8, 8, 3),
+                      (150, 16, 36), (400, 4, 30)):
+        for restart in (4, 100):
+            g, b = C.c_int(0), C.c_int(0)
+            rc = lib.ttipm_lgmres_plan(ineq, r, R, 4, s, restart, C.byref(g), C.byref(b))
+            assert rc in (0, 4), (r, R, s, restart, rc)
+            if rc == 0:
+                assert 1 <= g.value <= 148 and 0 < b.value <= 227 * 1024, (r, R, s, restart, g.value, b.value)
+print("ok")
+'''.replace("ROOT", repr(os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))))
+    env = dict(os.environ, TTIPM_EMU_SMS="148")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
