@@ -37,7 +37,7 @@
 
 namespace ttipm {
 
-#define TT_QR_PB 8
+#define TT_QR_PB 16
 #define TT_LIN_HDR 72          // doubles of per-batch flags ahead of the batch workspaces
 #define TT_LIN_REG 16          // register-resident vector length = 32 * TT_LIN_REG
 
@@ -72,6 +72,8 @@ struct LinParams {
     int nbatch;
 };
 
+TT_DEV long long lin_now_raw();
+
 struct LinCtx {
     const LinParams& p;
     double* smem;
@@ -99,6 +101,9 @@ struct LinCtx {
         if (p.cluster) cluster_sync_all();
         else grid_sync(barrier, epoch);
     }
+    // phase timers only when the caller asked for the info record: a %globaltimer read is not free and the Jacobi loop
+    // would take seven of them per round
+    TT_DEVM long long now() const { return p.info ? lin_now_raw() : 0; }
 };
 
 // the kernel's dynamic shared memory, re-derived where it is used heavily so that the compiler keeps the
@@ -109,14 +114,14 @@ TT_DEV double* lin_smem() {
 }
 
 #ifndef TTIPM_EMU
-TT_DEV long long lin_now() {
+TT_DEV long long lin_now_raw() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 TT_DEV double lin_rsqrt(double x) { return rsqrt(x); }
 #else
-TT_DEV long long lin_now() { return 0; }
+TT_DEV long long lin_now_raw() { return 0; }
 TT_DEV double lin_rsqrt(double x) { return 1.0 / sqrt(x); }
 #endif
 
@@ -225,9 +230,9 @@ TT_DEV void lin_qr_factor(LinCtx& c, double* W, double* tau, int Mq, int Nq, int
     for (int p0 = 0; p0 < K; p0 += TT_QR_PB) {
         const int pw = imin(TT_QR_PB, K - p0), rows = Mq - p0;
         __syncthreads();
-        const long long tq0 = lin_now();
+        const long long tq0 = c.now();
         lin_load_panel(c, W, nullptr, ld, Mq, p0, pw, false, P, taus, ldp);
-        const long long tq1 = lin_now();
+        const long long tq1 = c.now();
         // Panel factorisation: every warp derives reflector j from column j redundantly (no broadcast, no serial
         // section), warp w then updates panel columns j + 1 + w, ...; the tails stay unscaled until the panel is done,
         // so a column step is one block barrier.
@@ -289,7 +294,7 @@ TT_DEV void lin_qr_factor(LinCtx& c, double* W, double* tau, int Mq, int Nq, int
             }
             if ((int)threadIdx.x < pw) tau[p0 + threadIdx.x] = taus[threadIdx.x];
         }
-        const long long tq2 = lin_now();
+        const long long tq2 = c.now();
         for (int cc = p0 + pw + c.gw; cc < Nq; cc += c.GW) {
             double* x = W + (long)cc * ld + p0;
             if (rows <= 128) lin_trailing_col<4>(x, rows, P, ldp, taus, pw, lane);
@@ -300,13 +305,13 @@ TT_DEV void lin_qr_factor(LinCtx& c, double* W, double* tau, int Mq, int Nq, int
                     if (taus[j] != 0.0) lin_reflect_mem(x, 1, P + j * ldp, j, rows, taus[j], lane);
             }
         }
-        const long long tq3 = lin_now();
+        const long long tq3 = c.now();
         fence_proxy_async();                   // columns written here are read by the next panel's bulk copies
         c.sync();
         c.tq[0] += tq1 - tq0;
         c.tq[1] += tq2 - tq1;
         c.tq[2] += tq3 - tq2;
-        c.tq[3] += lin_now() - tq3;
+        c.tq[3] += c.now() - tq3;
     }
 }
 
@@ -573,7 +578,7 @@ TT_DEV int lin_jacobi(LinCtx& c, double* GJ, int K, int Mj, int* flags, long lon
                 const bool bvalid = b < nblk;
                 if (!bvalid && t != 0) continue;
                 const int na = imin(nb, K - a * nb), nbb = bvalid ? imin(nb, K - b * nb) : 0;
-                const long long t0 = lin_now();
+                const long long t0 = c.now();
                 __syncthreads();
                 // the rows of a block are contiguous: one bulk copy per block (slot q < nb -> block a, nb + q -> block b)
                 if (threadIdx.x == 0) {
@@ -587,7 +592,7 @@ TT_DEV int lin_jacobi(LinCtx& c, double* GJ, int K, int Mj, int* flags, long lon
                 }
                 mbar_wait(c.mbar, c.mphase);
                 c.mphase ^= 1u;
-                const long long t1 = lin_now();
+                const long long t1 = c.now();
                 int rot = 0;
                 if (t == 0 && nb > 1) {
                     // intra-block pairs of both blocks: round-robin over the nb (even) slots of each block
@@ -632,7 +637,7 @@ TT_DEV int lin_jacobi(LinCtx& c, double* GJ, int K, int Mj, int* flags, long lon
                 if (rot && lane == 0) rotated[0] = 1;
                 if ((rot & 2) && lane == 0) rotated[1] = 1;
                 __syncthreads();
-                const long long t2 = lin_now();
+                const long long t2 = c.now();
                 if (rotated[0]) {
                     double* ga = GJ + (long)a * nb * ldg;
                     double* gb = GJ + (long)b * nb * ldg;
@@ -645,14 +650,14 @@ TT_DEV int lin_jacobi(LinCtx& c, double* GJ, int K, int Mj, int* flags, long lon
                 }
                 tm[0] += t1 - t0;
                 tm[1] += t2 - t1;
-                tm[2] += lin_now() - t2;
+                tm[2] += c.now() - t2;
             }
-            const long long t3 = lin_now();
+            const long long t3 = c.now();
             fence_proxy_async();               // rows written through the generic proxy are read by bulk copies next round
-            const long long t4 = lin_now();
+            const long long t4 = c.now();
             c.sync();
             tm[2] += t4 - t3;
-            tm[3] += lin_now() - t4;
+            tm[3] += c.now() - t4;
         }
         // done: nothing rotated, or only small rotations (see lin_rot_level)
         if (ld_cg_i(&flags[sweeps]) == 0 || (c.p.early_exit && ld_cg_i(&flags[80 + sweeps]) == 0)) {
@@ -742,7 +747,7 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
     double* U = p.U + (long)batch * M * K;
     double* Wt = p.Wt + (long)batch * K * N;
     const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gth = (long)gridDim.x * blockDim.x;
-    const long long t_start = lin_now();
+    const long long t_start = c.now();
     long long tm[4] = {0, 0, 0, 0};
     if (threadIdx.x == 0) mbar_init(c.mbar, 1);
     // the sweep flags are zeroed here instead of by a memset node ahead of the launch (a memset between two kernels breaks
@@ -807,7 +812,7 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
         Mq = K;
         ldq = ldk;
     }
-    const long long t_qr = lin_now();
+    const long long t_qr = c.now();
     for (long i = gtid; i < (long)K * K; i += gth) {
         const long row = i / K, col = i % K;
         G[row * ldg + col] = row <= col ? ld_cg(Wq + row + col * ldq) : 0.0;
@@ -819,9 +824,9 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
     lin_apply_q(c, Wq, tq, ldq, Mq, K, K, 0, nullptr, 0, nullptr, Jt, ldg, 1);      // rows of Q^T (K x Mq), Mj == Mq
     fence_proxy_async();
     c.sync();
-    const long long t_q = lin_now();
+    const long long t_q = c.now();
     const int sweeps = p.resident ? lin_jacobi_resident(c, G, K, Mj) : lin_jacobi<NT>(c, G, K, Mj, flags, tm);
-    const long long t_jac = lin_now();
+    const long long t_jac = c.now();
     // singular values = row norms
     for (int i = c.gw; i < K; i += c.GW) {
         double s = 0.0;
@@ -871,7 +876,7 @@ TT_GLOBAL void __launch_bounds__(NT) k_linalg(const LinParams p) {
         info[7] = (int)tm[1];
         info[8] = (int)tm[2];
         info[9] = (int)tm[3];
-        info[10] = (int)(lin_now() - t_start);
+        info[10] = (int)(c.now() - t_start);
         info[11] = p.cluster;
         info[12] = (int)c.tq[0];
         info[13] = (int)c.tq[1];
