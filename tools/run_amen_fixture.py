@@ -36,7 +36,14 @@ def main():
     x0 = [np.asarray(c).copy() for c in g["x0"]] if g["x0"] is not None else None
     if x0 is not None:
         x0 = [np.asarray(c) for c in T.tt_rank_retraction(x0, [len(x0)] * (len(x0) - 1))]
-    s = NativeBlockAmen(g["A"], g["aliases"], g["transposes"], g["b"], g["ineq"], rt=rt)
+    profile = "--profile" in sys.argv
+    for rep in range(2 if profile else 1):         # --profile: one warm-up solve, then the instrumented one
+        np.random.set_state(g["rng_state"])
+        s = NativeBlockAmen(g["A"], g["aliases"], g["transposes"], g["b"], g["ineq"], rt=rt,
+                            stats={"profile": {}} if (profile and rep == 1) else None)
+        if rep == 0 and profile:
+            s.solve(g["termination_tol"], r_max=g["rank_restriction"], eps=g["eps"], nswp=g["inner_m"],
+                    x0=[c.copy() for c in x0] if x0 is not None else None, kick_rank=2, amen=True)
     rt.sync()
     t0 = time.perf_counter()
     x, res = s.solve(g["termination_tol"], r_max=g["rank_restriction"], eps=g["eps"], nswp=g["inner_m"], x0=x0, kick_rank=2,
@@ -45,6 +52,13 @@ def main():
     print(json.dumps(dict(seconds=time.perf_counter() - t0, res=res, sweeps=s.sweeps, ranks=list(s.ranks),
                           local_solves=len(s.trace), stats={k: v for k, v in s.stats.items() if not isinstance(v, list)})),
           flush=True)
+    if profile:
+        # CUDA events around every launch of the native driver: seconds, algorithmic flops (bytes for the memory-bound
+        # helpers), launches per kernel category
+        for name, (sec, work, nl) in s.native_profile.items():
+            if nl:
+                print(json.dumps(dict(category=name, ms=sec * 1e3, launches=int(nl), work=work,
+                                      rate_T_per_s=work / sec / 1e12 if sec > 0 else None)), flush=True)
 
 
 if __name__ == "__main__":
