@@ -37,7 +37,7 @@
 
 namespace ttipm {
 
-#define TT_QR_PB 16
+#define TT_QR_PB 8
 #define TT_LIN_HDR 72          // doubles of per-batch flags ahead of the batch workspaces
 #define TT_LIN_REG 16          // register-resident vector length = 32 * TT_LIN_REG
 
